@@ -1,0 +1,114 @@
+/* palantir_b200 C-ABI: the drop-in boundary for Palantir's diffusion-map and
+ * fate-probability hot path on B200 (sm_100a).
+ *
+ * The reference (dpeerlab/Palantir v1.4.4) is pure Python and has no FFI of its
+ * own: every entry point below replaces one third-party CPU library call site in
+ * the reference (cited per function as src/palantir/<file>:<line>); the Python
+ * mirror in palantir_b200/{utils,core}.py binds them through ctypes exactly as a
+ * maintainer of the reference would.
+ *
+ * Conventions: plain pointers and sizes, no framework types.  Every pointer is a
+ * DEVICE pointer unless its name ends in _host.  Matrices are row-major and
+ * contiguous.  `stream` is a cudaStream_t.  Every function returns 0 on success;
+ * otherwise a CUDA error code (> 0) or -1 (bad argument), with a message in
+ * pb200_last_error().  Nothing here allocates device memory: the caller owns
+ * every buffer, scratch included (sizes are stated per function).
+ * The parser in palantir_b200/_native.py reads the prototypes of this file:
+ * one prototype per statement, types limited to int / long long / double /
+ * pointers.
+ */
+#ifndef PALANTIR_B200_H
+#define PALANTIR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* pb200_last_error(void);
+int pb200_abi_version(void);
+int pb200_set_device(int dev);
+int pb200_device_sync(void);
+
+/* ---- exact kNN in PCA space: sklearn NearestNeighbors(brute).kneighbors, utils.py:404-407 ---- */
+
+/* Column means, centred FP32 k-major copy xt[d_pad][ld], FP32 score norms yn[ld] (+inf on padding),
+ * FP64 centred norms xcn[n], FP64 row norms of the original data xn64[n], max centred norm^2 rmax2[1].
+ * d <= 1024, d_pad % 16 == 0, ld % 256 == 0.  col_sums: d doubles of scratch. */
+int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, long long ld, double* col_sums,
+                      float* xt, float* yn, double* xcn, double* xn64, double* rmax2, void* stream);
+
+/* FP32 candidate generation: for query columns q0..q0+nq-1 of xtq keep the k_keep (<= 48) smallest
+ * scores |y|^2 - 2 x.y over all n_ref_pad references.  out_idx/out_score [nq][k_keep] ascending,
+ * out_thr[nq] = k_keep-th score (lower bound for every excluded reference; +inf if nothing excluded). */
+int pb200_knn_candidates_f32(const float* xtq, long long ldq, const float* xtr, long long ldr, const float* yn,
+                             int q0, int nq, long long n_ref_pad, int d_pad, int k_keep, int* out_idx,
+                             float* out_score, float* out_thr, void* stream);
+
+/* FP64 re-rank with the reference's expanded-form distance; out_idx/out_dist [nq][k] ascending by
+ * (distance, index); flag[nq] = 1 where the FP32 error bound cannot certify the row; n_flagged[1]. */
+int pb200_knn_rerank_f64(const void* x, int is_f64, const double* xn64, const double* xcn, const double* rmax2,
+                         long long n, int d, int q0, int nq, const int* cand, const float* thr32, int k_keep,
+                         int k, int* out_idx, double* out_dist, unsigned char* flag, int* n_flagged,
+                         void* stream);
+
+/* rows_out[0..counter) = indices (relative to q0) of flagged rows. */
+int pb200_knn_flagged_rows(const unsigned char* flag, int nq, int* rows_out, int* counter, void* stream);
+
+/* Exact FP64 brute force for the listed rows.  scratch: n_ctas * n doubles. */
+int pb200_knn_exact_rows_f64(const void* x, int is_f64, const double* xn64, long long n, int d, const int* rows,
+                             int n_rows, int q0, int k, double* scratch, int n_ctas, int* out_idx,
+                             double* out_dist, void* stream);
+
+/* Roofline probe: blocks x 1024 threads x iters x 16 FFMAs. */
+int pb200_fma_peak_f32(float* scratch, int blocks, int iters, void* stream);
+
+/* ---- exact kNN, direct FP64 differences (kd-tree equivalent): core.py:355-356, core.py:525-526 ---- */
+int pb200_knn_direct_f64(const double* data, long long n, int m, const double* query, const int* qrows, int q0,
+                         int nq, int k, int* out_idx, double* out_dist, void* stream);
+
+/* ---- adaptive kernel / CSR construction: utils.py:408-417, 440-446, 478-480 ---- */
+int pb200_knn_self_first(const int* idx, long long n, int kc, int* flag_out, void* stream);
+int pb200_adaptive_weights(const double* dist, long long n, int kc, int col0, int ka, double* w, void* stream);
+
+/* Symmetrise the arc list (idx[n][kc], w[n][kc-col0]); mode 0: K = W + W^T, mode 1: min(w_ij, w_ji).
+ * Scratch: indeg[n], ub[n], cursor[n] (int), off[n+1], bsum[n/1024+2] (long long),
+ * tcol/tval[2*n*(kc-col0)], row_nnz[n].  Output indptr[n+1]; nnz = indptr[n]. */
+int pb200_symmetrize_phase1(const int* idx, const double* w, long long n, int kc, int col0, int mode,
+                            int drop_self, int* indeg, int* ub, int* cursor, long long* off, long long* bsum,
+                            int* tcol, double* tval, int* row_nnz, int* indptr, void* stream);
+int pb200_symmetrize_phase2(long long n, const long long* off, const int* indptr, const int* tcol,
+                            const double* tval, int* indices, double* data, void* stream);
+
+int pb200_csr_row_sums(const int* indptr, const double* data, long long n, double* out, void* stream);
+/* op 0: 1/v (v != 0); op 1: v^p (v != 0); op 2: 1/sqrt(v) (v > 0, else 0); op 3: sqrt(v) */
+int pb200_vec_transform(double* v, long long n, int op, double p, void* stream);
+/* out[e] = (left[row] * data[e]) * right[col]; left / right may be NULL */
+int pb200_csr_scale(const int* indptr, const int* indices, const double* data, long long n, const double* left,
+                    const double* right, double* out, void* stream);
+/* flag_out[0] = number of entries (i,j,v) without a matching (j,i,v') with |v-v'| <= tol*max(|v|,|v'|) */
+int pb200_csr_is_symmetric(const int* indptr, const int* indices, const double* data, long long n, double tol,
+                           int* flag_out, void* stream);
+
+/* ---- eigensolver: scipy.sparse.linalg.eigs (ARPACK), utils.py:484 ---- */
+int pb200_csr_spmv_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                       const double* x, double* y, void* stream);
+int pb200_csr_spmm_f32(const int* indptr, const int* indices, const double* vals, long long n, const float* x,
+                       long long ldx, float* y, long long ldy, int g, void* stream);
+int pb200_vec_mul(const double* a, const double* b, double* out, long long n, void* stream);
+/* V0 = w / |w|.  scratch: partial[n/2048+1], tmp[1] */
+int pb200_lanczos_init(const double* w, long long n, double* V0, double* partial, double* tmp, void* stream);
+/* Lanczos steps j0..j0+nsteps-1 with full (CGS2) re-orthogonalisation; alpha[j], beta[j+1], V[j+1] written.
+ * scratch: w[n], h[j0+nsteps], partial[(j0+nsteps) * (n/2048+1)], tmp[1] */
+int pb200_lanczos_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                        double* V, long long ldv, int j0, int nsteps, double* alpha, double* beta, double* w,
+                        double* h, double* partial, double* tmp, void* stream);
+/* U[n][kk] = diag(scale) * sum_j V[j][:] Y[j][kk]  (scale may be NULL), kk <= 32 */
+int pb200_ritz_vectors(const double* V, long long ldv, int m, const double* Y, int kk, const double* scale,
+                       double* U, long long n, void* stream);
+/* unit-L2 columns.  scratch: partial[kk * (n/4096+1)], sumsq[kk] */
+int pb200_normalize_columns(double* A, long long n, int kk, double* partial, double* sumsq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PALANTIR_B200_H */

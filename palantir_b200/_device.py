@@ -1,0 +1,378 @@
+"""Device-side orchestration of the diffusion-map stages (kNN, kernel, eigensolver).
+
+Everything here works on CUDA tensors and calls the C-ABI kernels through
+``_native.call``; torch only allocates the buffers.  Host objects (scipy / pandas)
+are assembled by ``utils.py``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import call
+
+I32, I64, F32, F64, U8 = torch.int32, torch.int64, torch.float32, torch.float64, torch.uint8
+
+# timings of the last run, filled when PROFILE is a dict (bench.py sets it)
+PROFILE: Optional[dict] = None
+
+
+def _dev():
+    return _native.require_cuda()
+
+
+def empty(shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=_dev())
+
+
+def zeros(shape, dtype):
+    return torch.zeros(shape, dtype=dtype, device=_dev())
+
+
+def to_device(a: np.ndarray) -> torch.Tensor:
+    """Host array -> device tensor (one H2D copy, through pinned staging for big arrays)."""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(_dev(), non_blocking=False)
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class _Timer:
+    """CUDA-event stage timer (only active when PROFILE is a dict)."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.setdefault("_events", []).append((self.name, self.e0, self.e1))
+        return False
+
+
+def stage(name):
+    return _Timer(name)
+
+
+def flush_profile():
+    """Resolve recorded events into PROFILE[name] = milliseconds (summed)."""
+    if PROFILE is None:
+        return
+    torch.cuda.synchronize()
+    for name, e0, e1 in PROFILE.pop("_events", []):
+        PROFILE[name] = PROFILE.get(name, 0.0) + e0.elapsed_time(e1)
+
+
+# ---------------------------------------------------------------------------
+# kNN
+# ---------------------------------------------------------------------------
+KNN_MAX_KEEP = 48
+
+
+def sklearn_uses_brute(n: int, d: int, n_neighbors: int) -> bool:
+    """The 'auto' rule of sklearn NearestNeighbors (sklearn/neighbors/_base.py:618-626):
+    brute force (FP64 expanded-form distances) iff d > 15 or n_neighbors >= n // 2,
+    otherwise a kd-tree (direct-difference distances)."""
+    return d > 15 or n_neighbors >= n // 2
+
+
+@dataclass
+class KnnPrep:
+    x: torch.Tensor          # original data [n, d] f32/f64
+    xt: torch.Tensor         # centred FP32 k-major copy [d_pad, ld]
+    yn: torch.Tensor
+    xcn: torch.Tensor
+    xn64: torch.Tensor
+    rmax2: torch.Tensor
+    n: int
+    d: int
+    d_pad: int
+    ld: int
+
+
+def knn_prepare(x: torch.Tensor) -> KnnPrep:
+    n, d = x.shape
+    if x.dtype not in (F32, F64):
+        raise TypeError("kNN input must be float32 or float64")
+    d_pad = max(16, round_up(d, 16))
+    ld = round_up(n, 256)
+    xt = empty((d_pad, ld), F32)
+    yn = empty((ld,), F32)
+    xcn = empty((n,), F64)
+    xn64 = empty((n,), F64)
+    rmax2 = empty((1,), F64)
+    col_sums = empty((d,), F64)
+    call("pb200_knn_prepare", x, int(x.dtype == F64), n, d, d_pad, ld, col_sums, xt, yn, xcn, xn64, rmax2)
+    return KnnPrep(x, xt, yn, xcn, xn64, rmax2, n, d, d_pad, ld)
+
+
+def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
+                 slack: int = 12) -> Tuple[torch.Tensor, torch.Tensor, dict]:
+    """k nearest references (self included) of query rows q0..q0+nq-1, sklearn brute
+    semantics.  Returns (idx int32 [nq,k], dist f64 [nq,k], stats).  q0 % 256 == 0."""
+    n, d = prep.n, prep.d
+    nq = n - q0 if nq is None else nq
+    if k > n:
+        raise ValueError("k > number of points")
+    out_idx = empty((nq, k), I32)
+    out_dist = empty((nq, k), F64)
+    stats = {"flagged": 0, "k_keep": 0}
+    if nq == 0:
+        return out_idx, out_dist, stats
+    if k > KNN_MAX_KEEP:
+        # wider than the candidate buffers: exact FP64 brute force for every row
+        rows = torch.arange(nq, dtype=I32, device=out_idx.device)
+        _knn_exact_rows(prep, rows, nq, q0, k, out_idx, out_dist)
+        stats["flagged"] = nq
+        return out_idx, out_dist, stats
+    k_keep = min(KNN_MAX_KEEP, k + slack)
+    stats["k_keep"] = k_keep
+    cand = empty((nq, k_keep), I32)
+    score = empty((nq, k_keep), F32)
+    thr = empty((nq,), F32)
+    with stage("knn_candidates"):
+        call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.xt, prep.ld, prep.yn, q0, nq, prep.ld,
+             prep.d_pad, k_keep, cand, score, thr)
+    flag = empty((nq,), U8)
+    n_flagged = empty((1,), I32)
+    with stage("knn_rerank"):
+        call("pb200_knn_rerank_f64", prep.x, int(prep.x.dtype == F64), prep.xn64, prep.xcn, prep.rmax2, n, d,
+             q0, nq, cand, thr, k_keep, k, out_idx, out_dist, flag, n_flagged)
+    nf = int(n_flagged.item())
+    stats["flagged"] = nf
+    if nf > 0:
+        rows = empty((nq,), I32)
+        counter = empty((1,), I32)
+        call("pb200_knn_flagged_rows", flag, nq, rows, counter)
+        with stage("knn_exact_rows"):
+            _knn_exact_rows(prep, rows, nf, q0, k, out_idx, out_dist)
+    return out_idx, out_dist, stats
+
+
+def _knn_exact_rows(prep: KnnPrep, rows, n_rows, q0, k, out_idx, out_dist):
+    n_ctas = max(1, min(n_rows, 148))
+    scratch = empty((n_ctas, prep.n), F64)
+    call("pb200_knn_exact_rows_f64", prep.x, int(prep.x.dtype == F64), prep.xn64, prep.n, prep.d, rows, n_rows,
+         q0, k, scratch, n_ctas, out_idx, out_dist)
+
+
+def knn_direct(data: torch.Tensor, k: int, q0: int = 0, nq: Optional[int] = None,
+               query: Optional[torch.Tensor] = None, qrows: Optional[torch.Tensor] = None):
+    """Exact FP64 direct-difference kNN (kd-tree equivalent), m <= 16 columns."""
+    n, m = data.shape
+    if data.dtype != F64:
+        raise TypeError("knn_direct needs float64 data")
+    query = data if query is None else query
+    if qrows is not None:
+        nq = qrows.numel()
+    elif nq is None:
+        nq = query.shape[0] - q0
+    out_idx = empty((nq, k), I32)
+    out_dist = empty((nq, k), F64)
+    with stage("knn_direct"):
+        call("pb200_knn_direct_f64", data, n, m, query, qrows, q0, nq, k, out_idx, out_dist)
+    return out_idx, out_dist
+
+
+def knn_like_sklearn(x: torch.Tensor, n_neighbors: int, q0: int = 0, nq: Optional[int] = None):
+    """Dispatch exactly as sklearn's algorithm='auto' would (see sklearn_uses_brute)."""
+    n, d = x.shape
+    if sklearn_uses_brute(n, d, n_neighbors):
+        prep = knn_prepare(x)
+        idx, dist, stats = knn_expanded(prep, n_neighbors, q0, nq)
+        stats["method"] = "expanded"
+        return idx, dist, stats
+    data = x if x.dtype == F64 else x.to(F64)
+    idx, dist = knn_direct(data.contiguous(), n_neighbors, q0, nq)
+    return idx, dist, {"method": "direct", "flagged": 0}
+
+
+# ---------------------------------------------------------------------------
+# CSR construction
+# ---------------------------------------------------------------------------
+@dataclass
+class DeviceCSR:
+    indptr: torch.Tensor    # int32 [n+1]
+    indices: torch.Tensor   # int32 [nnz]
+    data: torch.Tensor      # f64 [nnz]
+    n: int
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indices.numel())
+
+
+def symmetrize(idx: torch.Tensor, w: torch.Tensor, col0: int, mode: int, drop_self: bool) -> DeviceCSR:
+    """Union-pattern symmetrisation of the arc list (idx[n,kc], w[n,kc-col0]):
+    mode 0 -> w_ij + w_ji, mode 1 -> min(w_ij, w_ji).  Sorted columns."""
+    n, kc = idx.shape
+    keff = kc - col0
+    indeg = empty((n,), I32)
+    ub = empty((n,), I32)
+    cursor = empty((n,), I32)
+    off = empty((n + 1,), I64)
+    bsum = empty((n // 1024 + 3,), I64)
+    tcol = empty((2 * n * keff,), I32)
+    tval = empty((2 * n * keff,), F64)
+    row_nnz = empty((n,), I32)
+    indptr = empty((n + 1,), I32)
+    call("pb200_symmetrize_phase1", idx, w, n, kc, col0, mode, int(drop_self), indeg, ub, cursor, off, bsum,
+         tcol, tval, row_nnz, indptr)
+    nnz = int(indptr[n].item())
+    indices = empty((nnz,), I32)
+    data = empty((nnz,), F64)
+    call("pb200_symmetrize_phase2", n, off, indptr, tcol, tval, indices, data)
+    return DeviceCSR(indptr, indices, data, n)
+
+
+def adaptive_kernel(idx: torch.Tensor, dist: torch.Tensor, knn: int, alpha: float) -> DeviceCSR:
+    """utils.py:408-417,440-446 on the device from a neighbour table that includes self."""
+    n, kc = idx.shape
+    col0 = 0
+    if kc > 1:
+        flag = empty((1,), I32)
+        call("pb200_knn_self_first", idx, n, kc, flag)
+        col0 = 1 if int(flag.item()) == 0 else 0
+    keff = kc - col0
+    ka = max(1, min(int(math.floor(knn / 3)), keff))
+    w = empty((n, keff), F64)
+    with stage("kernel_build"):
+        call("pb200_adaptive_weights", dist, n, kc, col0, ka, w)
+        kern = symmetrize(idx, w, col0, 0, False)
+        if alpha > 0:
+            deg = empty((n,), F64)
+            call("pb200_csr_row_sums", kern.indptr, kern.data, n, deg)
+            call("pb200_vec_transform", deg, n, 1, float(-alpha))
+            out = empty((kern.nnz,), F64)
+            call("pb200_csr_scale", kern.indptr, kern.indices, kern.data, n, deg, deg, out)
+            kern = DeviceCSR(kern.indptr, kern.indices, out, n)
+    return kern
+
+
+def csr_from_host(m) -> DeviceCSR:
+    """scipy CSR -> device (int32 indices, float64 values, sorted columns)."""
+    m = m.tocsr()
+    if not m.has_sorted_indices:
+        m = m.sorted_indices()
+    if m.nnz >= 2 ** 31:
+        raise ValueError("kernel has >= 2^31 stored entries")
+    return DeviceCSR(to_device(m.indptr.astype(np.int32, copy=False)),
+                     to_device(m.indices.astype(np.int32, copy=False)),
+                     to_device(m.data.astype(np.float64, copy=False)), m.shape[0])
+
+
+def csr_to_host(c: DeviceCSR, data: Optional[torch.Tensor] = None):
+    from scipy.sparse import csr_matrix
+
+    vals = (c.data if data is None else data).cpu().numpy()
+    return csr_matrix((vals, c.indices.cpu().numpy(), c.indptr.cpu().numpy()), shape=(c.n, c.n))
+
+
+# ---------------------------------------------------------------------------
+# eigensolver
+# ---------------------------------------------------------------------------
+class NotSymmetricError(NotImplementedError):
+    pass
+
+
+def transition_and_symmetric(kern: DeviceCSR):
+    """Row sums D, T = D^-1 K values, S = D^-1/2 K D^-1/2 values, D^-1/2, D^1/2."""
+    n = kern.n
+    deg = empty((n,), F64)
+    call("pb200_csr_row_sums", kern.indptr, kern.data, n, deg)
+    inv = deg.clone()
+    call("pb200_vec_transform", inv, n, 0, 0.0)
+    tvals = empty((kern.nnz,), F64)
+    call("pb200_csr_scale", kern.indptr, kern.indices, kern.data, n, inv, None, tvals)
+    dis = deg.clone()
+    call("pb200_vec_transform", dis, n, 2, 0.0)
+    svals = empty((kern.nnz,), F64)
+    call("pb200_csr_scale", kern.indptr, kern.indices, kern.data, n, dis, dis, svals)
+    dsq = deg.clone()
+    call("pb200_vec_transform", dsq, n, 3, 0.0)
+    return tvals, svals, dis, dsq
+
+
+def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start: torch.Tensor, k: int,
+                 tol: float = 1e-11, batch: int = 20, max_basis: Optional[int] = None):
+    """Largest-magnitude k eigenpairs of S (= those of T) by symmetric Lanczos with
+    full re-orthogonalisation.  Returns (eigenvalues desc [k] numpy, U device [n,k] =
+    unit-L2 columns of D^-1/2 u, info dict).
+
+    The small tridiagonal eigenproblem (m x m, m ~ a few hundred) is solved on the
+    host between batches of device steps -- control logic, like ARPACK's own
+    dseupd; all O(N) work stays on the device."""
+    from scipy.linalg import eigh_tridiagonal
+
+    n, nnz = kern.n, kern.nnz
+    if not (0 < k < n):
+        raise ValueError("need 0 < k < n eigenpairs")
+    if max_basis is None:
+        # keep the basis under ~40 GB
+        max_basis = int(min(n, max(4 * k + 40, min(2048, (40 << 30) // (8 * n)))))
+    max_basis = min(max_basis, n)
+    ld = n
+    nblk = n // 2048 + 1
+    V = empty((max_basis + 1, ld), F64)
+    alpha = zeros((max_basis + 1,), F64)
+    beta = zeros((max_basis + 2,), F64)
+    w = empty((n,), F64)
+    h = empty((max_basis + 1,), F64)
+    partial = empty(((max_basis + 1) * nblk,), F64)
+    tmp = empty((1,), F64)
+    call("pb200_lanczos_init", start, n, V, partial, tmp)
+    m = 0
+    info = {"converged": False}
+    theta = yvec = None
+    while m < max_basis:
+        steps = min(batch, max_basis - m)
+        with stage("lanczos_steps"):
+            call("pb200_lanczos_steps", kern.indptr, kern.indices, svals, n, nnz, V, ld, m, steps, alpha, beta, w,
+                 h, partial, tmp)
+        m += steps
+        if m < k + 1 and m < max_basis:
+            continue
+        a = alpha[:m].cpu().numpy()
+        b = beta[1:m + 1].cpu().numpy()          # b[j] = beta_{j+1}
+        theta_all, y_all = eigh_tridiagonal(a, b[:m - 1])
+        order = np.argsort(-np.abs(theta_all))[:k]
+        resid = np.abs(b[m - 1] * y_all[m - 1, order])
+        theta, yvec = theta_all[order], y_all[:, order]
+        info.update(steps=m, max_resid=float(resid.max()))
+        exhausted = (m >= n) or (b[m - 1] <= 1e-14 * max(1.0, np.abs(theta_all).max()))
+        if np.all(resid <= tol * np.maximum(np.abs(theta), 1e-3)) or exhausted:
+            info["converged"] = True
+            break
+    if not info["converged"]:
+        raise RuntimeError(
+            f"Lanczos did not converge in {m} steps (max residual {info.get('max_resid')}); "
+            "raise max_basis")
+    srt = np.argsort(-theta)
+    theta, yvec = theta[srt], np.ascontiguousarray(yvec[:, srt])
+    U = empty((n, k), F64)
+    with stage("ritz_vectors"):
+        call("pb200_ritz_vectors", V, ld, m, to_device(yvec), k, dis, U, n)
+        part2 = empty((k * (n // 4096 + 1),), F64)
+        sumsq = empty((k,), F64)
+        call("pb200_normalize_columns", U, n, k, part2, sumsq)
+    return theta, U, info
+
+
+def check_symmetric(kern: DeviceCSR, tol: float = 1e-12) -> bool:
+    flag = empty((1,), I32)
+    call("pb200_csr_is_symmetric", kern.indptr, kern.indices, kern.data, kern.n, tol, flag)
+    return int(flag.item()) == 0

@@ -1,0 +1,99 @@
+// Shared helpers for the palantir_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace pb200 {
+
+// Error plumbing: every C-ABI entry point returns 0 or a negative/CUDA code and
+// records a message retrievable through pb200_last_error().
+void set_error(const char* where, cudaError_t e);
+void set_error_msg(const char* msg);
+
+#define PB_CHECK_LAUNCH(name)                                  \
+  do {                                                         \
+    cudaError_t _e = cudaGetLastError();                       \
+    if (_e != cudaSuccess) { pb200::set_error(name, _e); return (int)_e; } \
+  } while (0)
+
+#define PB_CHECK(call)                                         \
+  do {                                                         \
+    cudaError_t _e = (call);                                   \
+    if (_e != cudaSuccess) { pb200::set_error(#call, _e); return (int)_e; } \
+  } while (0)
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier / bulk-copy (TMA engine, 1-D) PTX wrappers --------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t a = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-B aligned),
+// completion counted on an mbarrier in the same CTA.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- warp helpers -----------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Order-preserving map float -> uint32 (total order incl. negatives, +inf last).
+__device__ __forceinline__ uint32_t f32_ordered(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_ordered(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// atomicMin on non-negative doubles through their bit patterns (order preserving
+// for x >= 0, +inf included).
+__device__ __forceinline__ double atomic_min_pos_f64(double* addr, double v) {
+  unsigned long long old =
+      atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+  return __longlong_as_double((long long)old);
+}
+
+}  // namespace pb200

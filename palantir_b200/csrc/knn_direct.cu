@@ -1,0 +1,120 @@
+// Exact FP64 kNN with direct differences, for low-dimensional spaces (m <= 16).
+//
+// Replaces sklearn's kd-tree NearestNeighbors at src/palantir/core.py:355-356
+// (multiscale space, all cells) and core.py:525-526 (waypoints), and the
+// kd-tree branch of utils.py:404-407 when the PCA input has <= 15 columns.
+// The kd-tree's leaf distance is rdist = sum_c (x_c - y_c)^2 accumulated in
+// dimension order with separate multiply and add, then sqrt; the kernel does the
+// same in FP64 with contraction disabled (__dmul_rn / __dadd_rn), so the edge
+// weights are bit-equal.  Self is included (distance 0).
+// Ranking is by (distance, index).
+//
+// One thread owns one query row: coordinates in registers, its k-best list in
+// local memory (L1-resident; after warm-up an insertion happens ~k ln(N/k) times
+// per row), reference points streamed through shared memory in 128-point tiles
+// and read as warp-wide broadcasts.
+#include "common.cuh"
+
+namespace pb200 {
+
+constexpr int KD_ROWS = 128;  // query rows per CTA (one per thread)
+constexpr int KD_TILE = 128;  // reference points per shared-memory tile
+constexpr int KD_KMAX = 64;
+
+template <int M>
+__global__ void __launch_bounds__(KD_ROWS) knn_direct_kernel(const double* __restrict__ data, long long n,
+                                                             const double* __restrict__ query,
+                                                             const int* __restrict__ qrows, int q0, int nq,
+                                                             int k, int* __restrict__ out_idx,
+                                                             double* __restrict__ out_dist) {
+  __shared__ double tile[KD_TILE][M];
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x * KD_ROWS + tid;
+  const bool active = q < nq;
+  double x[M];
+  {
+    // query coordinates: either rows q0.. of `query`, or gathered rows qrows[q]
+    long long src = active ? (qrows ? (long long)qrows[q] : (long long)q0 + q) : 0;
+#pragma unroll
+    for (int c = 0; c < M; ++c) x[c] = query[src * M + c];
+  }
+  double bd[KD_KMAX];
+  int bi[KD_KMAX];
+  for (int s = 0; s < k; ++s) { bd[s] = INFINITY; bi[s] = -1; }
+  double worst = INFINITY;
+
+  for (long long t0 = 0; t0 < n; t0 += KD_TILE) {
+    __syncthreads();
+    for (int e = tid; e < KD_TILE * M; e += KD_ROWS) {
+      const long long g = t0 * M + e;
+      (&tile[0][0])[e] = g < n * M ? data[g] : 0.0;
+    }
+    __syncthreads();
+    const int lim = (int)((n - t0) < KD_TILE ? (n - t0) : KD_TILE);
+    if (active) {
+#pragma unroll 4
+      for (int j = 0; j < lim; ++j) {
+        double r = 0.0;
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          const double df = __dsub_rn(x[c], tile[j][c]);
+          r = __dadd_rn(r, __dmul_rn(df, df));
+        }
+        if (r < worst) {
+          // sorted insertion (ascending); ties keep the earlier (lower) index first
+          int pos = k - 1;
+          while (pos > 0 && bd[pos - 1] > r) {
+            bd[pos] = bd[pos - 1];
+            bi[pos] = bi[pos - 1];
+            --pos;
+          }
+          bd[pos] = r;
+          bi[pos] = (int)(t0 + j);
+          worst = bd[k - 1];
+        }
+      }
+    }
+  }
+  if (active) {
+    for (int s = 0; s < k; ++s) {
+      out_idx[(long long)q * k + s] = bi[s];
+      out_dist[(long long)q * k + s] = sqrt(bd[s]);
+    }
+  }
+}
+
+template <int M>
+static int launch_direct(const double* data, long long n, const double* query, const int* qrows, int q0, int nq,
+                         int k, int* out_idx, double* out_dist, cudaStream_t st) {
+  knn_direct_kernel<M><<<div_up(nq, KD_ROWS), KD_ROWS, 0, st>>>(data, n, query, qrows, q0, nq, k, out_idx,
+                                                                out_dist);
+  PB_CHECK_LAUNCH("knn_direct_kernel");
+  return 0;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" {
+
+// data: n x m row-major FP64 (reference set).  Queries are rows q0..q0+nq-1 of
+// `query` (same m), or, when qrows != NULL, rows qrows[0..nq-1] of `query`.
+int pb200_knn_direct_f64(const double* data, long long n, int m, const double* query, const int* qrows, int q0,
+                         int nq, int k, int* out_idx, double* out_dist, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m < 1 || m > 16 || k < 1 || k > KD_KMAX || k > n) {
+    set_error_msg("pb200_knn_direct_f64: need 1 <= m <= 16 and 1 <= k <= min(64, n)");
+    return -1;
+  }
+  if (nq <= 0) return 0;
+  switch (m) {
+#define PB_CASE(M) case M: return launch_direct<M>(data, n, query, qrows, q0, nq, k, out_idx, out_dist, st);
+    PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
+    PB_CASE(9) PB_CASE(10) PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15) PB_CASE(16)
+#undef PB_CASE
+  }
+  return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,447 @@
+// Exact kNN in PCA space, stage 1: FP32 candidate generation.
+//
+// Replaces the distance contraction + heap of sklearn's brute-force
+// NearestNeighbors.kneighbors that the reference calls at
+// src/palantir/utils.py:404-407.  The ranking value is
+//     s(i,j) = |y_j|^2 - 2 x_i . y_j          (= d^2(i,j) - |x_i|^2)
+// computed with FP32 FMAs on mean-centred, FP32-rounded coordinates.  The kernel
+// keeps, per query row, the K_keep (> k) smallest s and reports the K_keep-th
+// value as a threshold; the FP64 re-rank (knn_rerank.cu) recomputes the
+// reference's FP64 expanded-form distances for those candidates, takes the top
+// k, and proves with an FP32 error bound that no excluded point can belong to the
+// true top-k (rows that cannot be proven are redone exactly in FP64).
+//
+// Layout: coordinates are stored k-major ("XT"): XT[c * ld + i] is coordinate c
+// of point i, ld a multiple of 256, d padded with zero rows to a multiple of 16.
+// A CTA owns 256 query rows and streams every 128-point reference tile through a
+// 3-stage shared-memory ring filled by the TMA engine (cp.async.bulk, one elected
+// thread, mbarrier full/empty pairs).  16 consumer warps each own 16
+// query rows x 128 reference columns (8x8 register micro-tile per thread), so the
+// top-K lists of a row are only ever touched by one warp and the selection needs
+// no CTA-wide barrier.  One CTA per SM (512 threads, <=128 registers); lane 0 of
+// warp 0 doubles as the TMA producer (a 17th warp would cap registers at 96).
+#include "common.cuh"
+
+namespace pb200 {
+
+constexpr int KNN_BM = 256;       // query rows per CTA
+constexpr int KNN_BN = 128;       // reference points per tile
+constexpr int KNN_DK = 16;        // coordinates per pipeline stage
+constexpr int KNN_NST = 3;        // pipeline stages
+constexpr int KNN_CAP = 64;       // per-row candidate buffer capacity
+constexpr int KNN_HIGH = 56;      // compaction trigger
+constexpr int KNN_MAX_KEEP = 48;  // max K_keep
+constexpr int KNN_CONSUMER_WARPS = 16;
+constexpr int KNN_THREADS = KNN_CONSUMER_WARPS * 32;
+
+struct KnnStage {
+  float a[KNN_DK][KNN_BM];
+  float b[KNN_DK][KNN_BN];
+  float yn[KNN_BN];
+};
+constexpr uint32_t KNN_STAGE_TX = KNN_DK * KNN_BM * 4 + KNN_DK * KNN_BN * 4;
+
+struct KnnSmem {
+  KnnStage st[KNN_NST];
+  unsigned long long buf[KNN_BM][KNN_CAP];
+  int cnt[KNN_BM];
+  float thr[KNN_BM];
+  uint64_t full[KNN_NST];
+  uint64_t empty[KNN_NST];
+};
+
+struct KnnParams {
+  const float* xtq;  // query coordinates, k-major
+  long long ldq;
+  const float* xtr;  // reference coordinates, k-major
+  long long ldr;
+  const float* yn;   // |y_j|^2 per reference (FP32, +inf on padding)
+  int q0;            // first query column in xtq (multiple of 256)
+  int nq;            // number of query rows handled by this launch
+  int n_ref_tiles;   // ldr-padded reference count / 128
+  int kch;           // d_pad / 16
+  int k_keep;
+  int* out_idx;      // [nq][k_keep]
+  float* out_score;  // [nq][k_keep]
+  float* out_thr;    // [nq]
+};
+
+__device__ __forceinline__ unsigned long long pack_entry(float s, int idx) {
+  return ((unsigned long long)f32_ordered(s) << 32) | (unsigned int)idx;
+}
+
+// Warp-collective: keep the k_keep smallest entries of a row's buffer (rank by
+// counting; keys are unique because the index is part of the key).
+__device__ __forceinline__ void compact_row(KnnSmem& sm, int row, int k_keep, int lane) {
+  int c = sm.cnt[row];
+  c = c < KNN_CAP ? c : KNN_CAP;
+  unsigned long long e0 = lane < c ? sm.buf[row][lane] : ~0ull;
+  unsigned long long e1 = lane + 32 < c ? sm.buf[row][lane + 32] : ~0ull;
+  int r0 = 0, r1 = 0;
+#pragma unroll 8
+  for (int j = 0; j < 32; ++j) {
+    unsigned long long o0 = __shfl_sync(0xffffffffu, e0, j);
+    unsigned long long o1 = __shfl_sync(0xffffffffu, e1, j);
+    r0 += (o0 < e0) + (o1 < e0);
+    r1 += (o0 < e1) + (o1 < e1);
+  }
+  __syncwarp();
+  if (lane < c && r0 < k_keep) sm.buf[row][r0] = e0;
+  if (lane + 32 < c && r1 < k_keep) sm.buf[row][r1] = e1;
+  if (c >= k_keep) {
+    if (lane < c && r0 == k_keep - 1) sm.thr[row] = f32_from_ordered((uint32_t)(e0 >> 32));
+    if (lane + 32 < c && r1 == k_keep - 1) sm.thr[row] = f32_from_ordered((uint32_t)(e1 >> 32));
+  }
+  if (lane == 0) sm.cnt[row] = c < k_keep ? c : k_keep;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const KnnParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  KnnSmem& sm = *reinterpret_cast<KnnSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int qbase = p.q0 + blockIdx.x * KNN_BM;  // column in xtq
+  const int row_local0 = blockIdx.x * KNN_BM;    // row in the output arrays
+
+  for (int r = tid; r < KNN_BM; r += KNN_THREADS) {
+    sm.cnt[r] = 0;
+    sm.thr[r] = INFINITY;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < KNN_NST; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], KNN_CONSUMER_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int T = p.n_ref_tiles;
+  const int KCH = p.kch;
+
+  // ---------------- producer state (warp 0, lane 0 drives the TMA engine) -------------
+  // The producer runs KNN_NST-1 chunks ahead of warp 0's own consumption; before
+  // refilling a stage it waits on that stage's "empty" barrier (all 16 warps done).
+  const bool is_producer = (tid == 0);
+  int p_t = 0, p_kc = 0, p_stage = 0;
+  uint32_t p_phase = 0;
+  auto produce = [&]() {
+    if (p_t >= T) return;
+    mbar_wait(&sm.empty[p_stage], p_phase ^ 1u);
+    const bool last = (p_kc == KCH - 1);
+    mbar_arrive_expect_tx(&sm.full[p_stage], KNN_STAGE_TX + (last ? KNN_BN * 4u : 0u));
+    const float* aq = p.xtq + (long long)(p_kc * KNN_DK) * p.ldq + qbase;
+    const float* br = p.xtr + (long long)(p_kc * KNN_DK) * p.ldr + (long long)p_t * KNN_BN;
+#pragma unroll
+    for (int k = 0; k < KNN_DK; ++k)
+      bulk_g2s(&sm.st[p_stage].a[k][0], aq + (long long)k * p.ldq, KNN_BM * 4, &sm.full[p_stage]);
+#pragma unroll
+    for (int k = 0; k < KNN_DK; ++k)
+      bulk_g2s(&sm.st[p_stage].b[k][0], br + (long long)k * p.ldr, KNN_BN * 4, &sm.full[p_stage]);
+    if (last) bulk_g2s(&sm.st[p_stage].yn[0], p.yn + (long long)p_t * KNN_BN, KNN_BN * 4, &sm.full[p_stage]);
+    if (++p_stage == KNN_NST) { p_stage = 0; p_phase ^= 1u; }
+    if (++p_kc == KCH) { p_kc = 0; ++p_t; }
+  };
+  if (is_producer) {
+    for (int s = 0; s < KNN_NST - 1; ++s) produce();
+  }
+
+  // ---------------- consumers ---------------------------------------------------------
+  const int r0 = warp * 16 + (lane >> 4) * 8;  // first of this thread's 8 rows (CTA-local)
+  const int c0 = (lane & 15) * 4;              // columns c0..c0+3 and 64+c0..64+c0+3
+  int stage = 0;
+  uint32_t phase = 0;
+  float acc[8][8];
+  float ynr[8];
+
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    for (int kc = 0; kc < KCH; ++kc) {
+      if (is_producer) produce();
+      mbar_wait(&sm.full[stage], phase);
+      const float* As = &sm.st[stage].a[0][0];
+      const float* Bs = &sm.st[stage].b[0][0];
+#pragma unroll
+      for (int k = 0; k < KNN_DK; ++k) {
+        const float4 a0 = *reinterpret_cast<const float4*>(As + k * KNN_BM + r0);
+        const float4 a1 = *reinterpret_cast<const float4*>(As + k * KNN_BM + r0 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN + c0);
+        const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN + 64 + c0);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (kc == KCH - 1) {
+        const float4 y0 = *reinterpret_cast<const float4*>(&sm.st[stage].yn[c0]);
+        const float4 y1 = *reinterpret_cast<const float4*>(&sm.st[stage].yn[64 + c0]);
+        ynr[0] = y0.x; ynr[1] = y0.y; ynr[2] = y0.z; ynr[3] = y0.w;
+        ynr[4] = y1.x; ynr[5] = y1.y; ynr[6] = y1.z; ynr[7] = y1.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[stage]);
+      if (++stage == KNN_NST) { stage = 0; phase ^= 1u; }
+    }
+
+    // ---- selection: fast reject against the per-row threshold ----
+    bool hit = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float thr = sm.thr[r0 + i];
+      float m = fmaf(-2.f, acc[i][0], ynr[0]);
+#pragma unroll
+      for (int j = 1; j < 8; ++j) m = fminf(m, fmaf(-2.f, acc[i][j], ynr[j]));
+      hit |= (m < thr);
+    }
+    if (__any_sync(0xffffffffu, hit)) {
+      const int colbase = t * KNN_BN;
+      for (;;) {
+        bool fail = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = r0 + i;
+          const float thr = sm.thr[row];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float s = fmaf(-2.f, acc[i][j], ynr[j]);
+            if (s < thr) {
+              const int pos = atomicAdd(&sm.cnt[row], 1);
+              if (pos < KNN_CAP) {
+                const int col = colbase + (j < 4 ? c0 + j : 64 + c0 + (j - 4));
+                sm.buf[row][pos] = pack_entry(s, col);
+                acc[i][j] = -INFINITY;  // s becomes +inf: never pushed twice
+              } else {
+                fail = true;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        for (int rr = 0; rr < 16; ++rr) {
+          const int row = warp * 16 + rr;
+          if (sm.cnt[row] >= KNN_HIGH) compact_row(sm, row, p.k_keep, lane);
+        }
+        if (!__any_sync(0xffffffffu, fail)) break;
+      }
+    }
+  }
+
+  // ---- emit: final sort of each row, ascending (score, index) ----
+  for (int rr = 0; rr < 16; ++rr) {
+    const int row = warp * 16 + rr;
+    const int grow = row_local0 + row;
+    if (grow >= p.nq) continue;  // warp-uniform
+    int c = sm.cnt[row];
+    c = c < KNN_CAP ? c : KNN_CAP;
+    const unsigned long long e0 = lane < c ? sm.buf[row][lane] : ~0ull;
+    const unsigned long long e1 = lane + 32 < c ? sm.buf[row][lane + 32] : ~0ull;
+    int q0r = 0, q1r = 0;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const unsigned long long o0 = __shfl_sync(0xffffffffu, e0, j);
+      const unsigned long long o1 = __shfl_sync(0xffffffffu, e1, j);
+      q0r += (o0 < e0) + (o1 < e0);
+      q1r += (o0 < e1) + (o1 < e1);
+    }
+    const int kk = p.k_keep;
+    int* oi = p.out_idx + (long long)grow * kk;
+    float* os = p.out_score + (long long)grow * kk;
+    if (lane < c && q0r < kk) { oi[q0r] = (int)(uint32_t)e0; os[q0r] = f32_from_ordered((uint32_t)(e0 >> 32)); }
+    if (lane + 32 < c && q1r < kk) { oi[q1r] = (int)(uint32_t)e1; os[q1r] = f32_from_ordered((uint32_t)(e1 >> 32)); }
+    for (int s = c + lane; s < kk; s += 32) { oi[s] = -1; os[s] = INFINITY; }
+    float thr_out = INFINITY;
+    if (c >= kk) {
+      // the kk-th smallest kept score bounds every excluded reference from below
+      float cand = -INFINITY;
+      if (lane < c && q0r == kk - 1) cand = f32_from_ordered((uint32_t)(e0 >> 32));
+      if (lane + 32 < c && q1r == kk - 1) cand = f32_from_ordered((uint32_t)(e1 >> 32));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cand = fmaxf(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+      thr_out = cand;
+    }
+    if (lane == 0) p.out_thr[grow] = thr_out;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Preparation: column means, centred FP32 k-major copy, norms.
+// ----------------------------------------------------------------------------
+template <typename T>
+__global__ void col_sums_kernel(const T* __restrict__ x, long long n, int d, double* __restrict__ sums) {
+  // block (32, 8); thread handles columns tx, tx+32, ... (<= 32 slots => d <= 1024)
+  double loc[32];
+#pragma unroll
+  for (int s = 0; s < 32; ++s) loc[s] = 0.0;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (long long r = (long long)blockIdx.x * 8 + ty; r < n; r += (long long)gridDim.x * 8) {
+    const T* row = x + r * d;
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+      const int c = tx + 32 * s;
+      if (c < d) loc[s] += (double)row[c];
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < 32; ++s) {
+    const int c = tx + 32 * s;
+    if (c < d && loc[s] != 0.0) atomicAdd(&sums[c], loc[s]);
+  }
+}
+
+// One block = 32 points.  Writes xt[c*ld + i] = (float)(x[i][c] - mean[c]) (0 on
+// padding), yn[i] = (float)sum_c xt^2 (+inf on padding rows), xcn[i] = the same
+// sum in FP64, xn64[i] = sum_c x[i][c]^2 in FP64 on the ORIGINAL values (the
+// reference's row norm), and the running max of xcn in *rmax2_bits.
+template <typename T>
+__global__ void knn_prep_kernel(const T* __restrict__ x, long long n, int d, int d_pad, long long ld,
+                                const double* __restrict__ sums, float* __restrict__ xt,
+                                float* __restrict__ yn, double* __restrict__ xcn, double* __restrict__ xn64,
+                                unsigned long long* __restrict__ rmax2_bits) {
+  __shared__ float tile[32][33];
+  __shared__ double part_c[8][32];
+  __shared__ double part_o[8][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+  const long long i0 = (long long)blockIdx.x * 32;
+  double accc[4] = {0, 0, 0, 0};  // rows ty, ty+8, ty+16, ty+24 (partial over this thread's columns)
+  double acco[4] = {0, 0, 0, 0};
+  const double inv_n = 1.0 / (double)n;
+  for (int cb = 0; cb < d_pad; cb += 32) {
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int r = ty + 8 * rr;
+      const long long i = i0 + r;
+      const int c = cb + tx;
+      float v = 0.f;
+      if (i < n && c < d) {
+        const double orig = (double)x[i * d + c];
+        v = (float)(orig - sums[c] * inv_n);
+        acco[rr] = fma(orig, orig, acco[rr]);
+        accc[rr] = fma((double)v, (double)v, accc[rr]);
+      }
+      tile[r][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int c = cb + ty + 8 * rr;
+      if (c < d_pad) xt[(long long)c * ld + i0 + tx] = tile[tx][ty + 8 * rr];
+    }
+    __syncthreads();
+  }
+  // reduce the per-thread partial norms across tx (columns) for each of the 4 rows
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const double sc = warp_sum(accc[rr]);
+    const double so = warp_sum(acco[rr]);
+    if (tx == 0) { part_c[ty][rr] = sc; part_o[ty][rr] = so; }
+  }
+  __syncthreads();
+  if (ty == 0) {
+    const int r = tx;  // row r = ty' + 8*rr  with ty' = r % 8, rr = r / 8
+    const double sc = part_c[r & 7][r >> 3];
+    const double so = part_o[r & 7][r >> 3];
+    const long long i = i0 + r;
+    if (i < n) {
+      yn[i] = (float)sc;
+      xcn[i] = sc;
+      xn64[i] = so;
+      atomicMax(rmax2_bits, (unsigned long long)__double_as_longlong(sc));
+    } else if (i < ld) {
+      yn[i] = INFINITY;
+    }
+  }
+}
+
+// Pure FFMA throughput probe (roofline denominator for the kNN stage).
+__global__ void fma_peak_kernel(float* out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = threadIdx.x * 1e-3f + i;
+  const float b = 1.0000001f, c = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) out[0] = s;
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" {
+
+int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, long long ld, double* col_sums,
+                      float* xt, float* yn, double* xcn, double* xn64, double* rmax2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d > 1024 || d_pad % KNN_DK != 0 || d_pad < d || ld % KNN_BM != 0 || ld < n) {
+    set_error_msg("pb200_knn_prepare: need d <= 1024, d_pad % 16 == 0, ld % 256 == 0, ld >= n");
+    return -1;
+  }
+  PB_CHECK(cudaMemsetAsync(col_sums, 0, sizeof(double) * d, st));
+  PB_CHECK(cudaMemsetAsync(rmax2, 0, sizeof(double), st));
+  const int gb = (int)((n + 7) / 8 < 4 * kSMs ? (n + 7) / 8 : 4 * kSMs);
+  dim3 blk(32, 8);
+  if (is_f64) col_sums_kernel<double><<<gb, blk, 0, st>>>((const double*)x, n, d, col_sums);
+  else        col_sums_kernel<float><<<gb, blk, 0, st>>>((const float*)x, n, d, col_sums);
+  PB_CHECK_LAUNCH("col_sums_kernel");
+  const int nb = (int)(ld / 32);
+  if (is_f64)
+    knn_prep_kernel<double><<<nb, blk, 0, st>>>((const double*)x, n, d, d_pad, ld, col_sums, xt, yn, xcn, xn64,
+                                                 (unsigned long long*)rmax2);
+  else
+    knn_prep_kernel<float><<<nb, blk, 0, st>>>((const float*)x, n, d, d_pad, ld, col_sums, xt, yn, xcn, xn64,
+                                                (unsigned long long*)rmax2);
+  PB_CHECK_LAUNCH("knn_prep_kernel");
+  return 0;
+}
+
+int pb200_knn_candidates_f32(const float* xtq, long long ldq, const float* xtr, long long ldr, const float* yn,
+                             int q0, int nq, long long n_ref_pad, int d_pad, int k_keep, int* out_idx,
+                             float* out_score, float* out_thr, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k_keep < 1 || k_keep > KNN_MAX_KEEP || q0 % KNN_BM != 0 || n_ref_pad % KNN_BN != 0 ||
+      d_pad % KNN_DK != 0 || d_pad < KNN_DK) {
+    set_error_msg("pb200_knn_candidates_f32: bad k_keep / alignment");
+    return -1;
+  }
+  if (nq <= 0) return 0;
+  const int tiles = div_up(nq, KNN_BM);
+  if ((long long)q0 + (long long)tiles * KNN_BM > ldq) {
+    set_error_msg("pb200_knn_candidates_f32: query tiles exceed ldq");
+    return -1;
+  }
+  KnnParams p;
+  p.xtq = xtq; p.ldq = ldq; p.xtr = xtr; p.ldr = ldr; p.yn = yn;
+  p.q0 = q0; p.nq = nq; p.n_ref_tiles = (int)(n_ref_pad / KNN_BN); p.kch = d_pad / KNN_DK; p.k_keep = k_keep;
+  p.out_idx = out_idx; p.out_score = out_score; p.out_thr = out_thr;
+  static bool attr_set = false;
+  const int smem = (int)sizeof(KnnSmem);
+  if (!attr_set) {
+    PB_CHECK(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  knn_candidates_kernel<<<tiles, KNN_THREADS, smem, st>>>(p);
+  PB_CHECK_LAUNCH("knn_candidates_kernel");
+  return 0;
+}
+
+// Launches `blocks` CTAs x 1024 threads, each thread doing iters*16 FFMAs.
+int pb200_fma_peak_f32(float* scratch, int blocks, int iters, void* stream) {
+  fma_peak_kernel<<<blocks, 1024, 0, (cudaStream_t)stream>>>(scratch, iters);
+  PB_CHECK_LAUNCH("fma_peak_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+// Symmetric Lanczos eigensolver pieces: CSR SpMV/SpMM and the dense vector
+// kernels of a fully re-orthogonalised Lanczos recurrence.
+//
+// Replaces scipy.sparse.linalg.eigs (ARPACK) at src/palantir/utils.py:484.  The
+// reference asks for the largest-magnitude eigenpairs of the row-stochastic
+// T = D^-1 K; T is similar to the symmetric S = D^-1/2 K D^-1/2, so the solver
+// runs symmetric Lanczos on S (eigenvalues identical, eigenvectors of T are
+// D^-1/2 u) -- SURVEY.md 7a step 4.
+//
+// The recurrence runs on the device with no host round trip per step: alpha and
+// beta stay in device memory and every kernel reads the scalars it needs from
+// there.  Re-orthogonalisation is classical Gram-Schmidt applied twice (CGS2):
+// h = V^T w, w -= V h, all basis vectors read with coalesced row-contiguous
+// loads; all reductions are two-stage and deterministic (no FP atomics).
+#include "common.cuh"
+
+namespace pb200 {
+
+// ---------------------------------------------------------------------------
+// SpMV: y = A x, CSR with FP64 values / int32 columns.  L lanes cooperate on a
+// row (L = 8, 16 or 32 chosen from the mean row length); the value and column
+// streams are read coalesced, x is gathered through L2.  HBM-bound:
+// 12 B/nnz + 4 B/row (indptr) + 8 B/row (y) + x once.
+// ---------------------------------------------------------------------------
+template <int L>
+__global__ void __launch_bounds__(256) csr_spmv_kernel(const int* __restrict__ indptr,
+                                                       const int* __restrict__ indices,
+                                                       const double* __restrict__ vals,
+                                                       const double* __restrict__ x, double* __restrict__ y,
+                                                       long long n) {
+  const int lane = threadIdx.x & (L - 1);
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  if (row >= n) return;  // whole sub-warp leaves together
+  const int beg = indptr[row], end = indptr[row + 1];
+  double s0 = 0.0, s1 = 0.0;
+  int e = beg + lane;
+  for (; e + L < end; e += 2 * L) {
+    const int c0 = indices[e], c1 = indices[e + L];
+    const double v0 = vals[e], v1 = vals[e + L];
+    s0 = fma(v0, __ldg(x + c0), s0);
+    s1 = fma(v1, __ldg(x + c1), s1);
+  }
+  if (e < end) s0 = fma(vals[e], __ldg(x + indices[e]), s0);
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, L);
+  if (lane == 0) y[row] = s;
+}
+
+// SpMM for MAGIC: Y[n][g] (+)= A X[n][g], FP32 dense operands, FP64 CSR values
+// converted on the fly (the reference casts T^t to float32, utils.py:791).
+// One warp per row; lanes stride over the g columns (coalesced X row reads).
+__global__ void __launch_bounds__(256) csr_spmm_f32_kernel(const int* __restrict__ indptr,
+                                                           const int* __restrict__ indices,
+                                                           const double* __restrict__ vals,
+                                                           const float* __restrict__ x, float* __restrict__ y,
+                                                           long long n, int g, long long ldx, long long ldy) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= n) return;
+  const int beg = indptr[row], end = indptr[row + 1];
+  for (int c0 = lane; c0 < g; c0 += 128) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int e = beg; e < end; ++e) {
+      const float v = (float)vals[e];
+      const float* xr = x + (long long)indices[e] * ldx;
+      a0 = fmaf(v, xr[c0], a0);
+      if (c0 + 32 < g) a1 = fmaf(v, xr[c0 + 32], a1);
+      if (c0 + 64 < g) a2 = fmaf(v, xr[c0 + 64], a2);
+      if (c0 + 96 < g) a3 = fmaf(v, xr[c0 + 96], a3);
+    }
+    float* yr = y + row * ldy;
+    yr[c0] = a0;
+    if (c0 + 32 < g) yr[c0 + 32] = a1;
+    if (c0 + 64 < g) yr[c0 + 64] = a2;
+    if (c0 + 96 < g) yr[c0 + 96] = a3;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dense vector kernels
+// ---------------------------------------------------------------------------
+constexpr int VB = 256;        // threads
+constexpr int VCHUNK = 2048;   // elements per block (8 per thread)
+
+// partial[c * nblk + b] = sum_{i in chunk b} V[c][i] * w[i],  c = 0..m-1
+__global__ void __launch_bounds__(VB) multi_dot_kernel(const double* __restrict__ V, long long ldv, int m,
+                                                       const double* __restrict__ w, long long n,
+                                                       double* __restrict__ partial) {
+  __shared__ double red[VB / 32];
+  const long long base = (long long)blockIdx.x * VCHUNK;
+  double wr[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const long long i = base + threadIdx.x + (long long)t * VB;
+    wr[t] = i < n ? w[i] : 0.0;
+  }
+  for (int c = 0; c < m; ++c) {
+    const double* v = V + (long long)c * ldv;
+    double s = 0.0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const long long i = base + threadIdx.x + (long long)t * VB;
+      if (i < n) s = fma(v[i], wr[t], s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+#pragma unroll
+      for (int q = 0; q < VB / 32; ++q) tot += red[q];
+      partial[(long long)c * gridDim.x + blockIdx.x] = tot;
+    }
+    __syncthreads();
+  }
+}
+
+// h[c] = sum_b partial[c][b]; optionally hacc[c] += h[c]
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int nblk, int m,
+                                       double* __restrict__ h, double* __restrict__ hacc) {
+  const int c = blockIdx.x;
+  if (c >= m) return;
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += partial[(long long)c * nblk + b];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) tot += red[q];
+    h[c] = tot;
+    if (hacc) hacc[c] += tot;
+  }
+}
+
+// w[i] -= sum_c h[c] V[c][i]
+__global__ void __launch_bounds__(VB) multi_axpy_kernel(const double* __restrict__ V, long long ldv, int m,
+                                                        const double* __restrict__ h, double* __restrict__ w,
+                                                        long long n) {
+  extern __shared__ double hs[];
+  for (int c = threadIdx.x; c < m; c += VB) hs[c] = h[c];
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * VCHUNK;
+  double acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.0;
+  for (int c = 0; c < m; ++c) {
+    const double* v = V + (long long)c * ldv;
+    const double hc = hs[c];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const long long i = base + threadIdx.x + (long long)t * VB;
+      if (i < n) acc[t] = fma(hc, v[i], acc[t]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const long long i = base + threadIdx.x + (long long)t * VB;
+    if (i < n) w[i] -= acc[t];
+  }
+}
+
+// out[i] = w[i] / sqrt(*nrm2)    (also records sqrt(*nrm2) into *beta_out if given)
+__global__ void scale_by_norm_kernel(const double* __restrict__ w, const double* __restrict__ nrm2,
+                                     double* __restrict__ out, long long n, double* __restrict__ beta_out) {
+  const double b = sqrt(*nrm2);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && beta_out) *beta_out = b;
+  if (i < n) out[i] = b > 0.0 ? w[i] / b : 0.0;
+}
+
+__global__ void vec_mul_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                               double* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] * b[i];
+}
+
+// U[i][c] = scale[i] * sum_j V[j][i] * Y[j][c],   c < kk <= 16, Y row-major m x kk
+template <int KK>
+__global__ void __launch_bounds__(256) ritz_combine_kernel(const double* __restrict__ V, long long ldv, int m,
+                                                           const double* __restrict__ Y,
+                                                           const double* __restrict__ scale,
+                                                           double* __restrict__ U, long long n, int kk) {
+  extern __shared__ double ys[];  // m * kk
+  for (int e = threadIdx.x; e < m * kk; e += 256) ys[e] = Y[e];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  double acc[KK];
+#pragma unroll
+  for (int c = 0; c < KK; ++c) acc[c] = 0.0;
+  for (int j = 0; j < m; ++j) {
+    const double v = V[(long long)j * ldv + i];
+#pragma unroll
+    for (int c = 0; c < KK; ++c)
+      if (c < kk) acc[c] = fma(v, ys[j * kk + c], acc[c]);
+  }
+  const double sc = scale ? scale[i] : 1.0;
+#pragma unroll
+  for (int c = 0; c < KK; ++c)
+    if (c < kk) U[i * kk + c] = sc * acc[c];
+}
+
+// partial[b][c] = sum_{i in block b} A[i][c]^2
+__global__ void __launch_bounds__(256) col_sumsq_kernel(const double* __restrict__ A, long long n, int kk,
+                                                        double* __restrict__ partial) {
+  __shared__ double red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double s[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) s[c] = 0.0;
+  const long long i0 = (long long)blockIdx.x * 4096;
+  for (int t = 0; t < 16; ++t) {
+    const long long i = i0 + threadIdx.x + t * 256;
+    if (i < n)
+      for (int c = 0; c < kk; ++c) { const double v = A[i * kk + c]; s[c] = fma(v, v, s[c]); }
+  }
+  for (int c = 0; c < kk; ++c) {
+    const double t = warp_sum(s[c]);
+    if (lane == 0) red[warp][c] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < kk) {
+    double tot = 0.0;
+    for (int q = 0; q < 8; ++q) tot += red[q][threadIdx.x];
+    partial[(long long)threadIdx.x * gridDim.x + blockIdx.x] = tot;
+  }
+}
+
+__global__ void col_scale_kernel(double* __restrict__ A, long long n, int kk, const double* __restrict__ sumsq) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * kk) return;
+  const int c = (int)(e % kk);
+  A[e] = A[e] / sqrt(sumsq[c]);
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+static int launch_spmv(const int* indptr, const int* indices, const double* vals, const double* x, double* y,
+                       long long n, long long nnz, cudaStream_t st) {
+  const double mean = n > 0 ? (double)nnz / (double)n : 0.0;
+  if (mean > 24.0) {
+    csr_spmv_kernel<16><<<div_up(n * 16, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n);
+  } else if (mean > 12.0) {
+    csr_spmv_kernel<8><<<div_up(n * 8, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n);
+  } else {
+    csr_spmv_kernel<4><<<div_up(n * 4, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n);
+  }
+  PB_CHECK_LAUNCH("csr_spmv_kernel");
+  return 0;
+}
+
+static int nrm2_into(const double* w, long long n, double* partial, double* out, cudaStream_t st) {
+  const int nblk = div_up(n, VCHUNK);
+  multi_dot_kernel<<<nblk, VB, 0, st>>>(w, 0, 1, w, n, partial);
+  PB_CHECK_LAUNCH("multi_dot_kernel(nrm2)");
+  reduce_partials_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, out, nullptr);
+  PB_CHECK_LAUNCH("reduce_partials_kernel(nrm2)");
+  return 0;
+}
+
+extern "C" {
+
+int pb200_csr_spmv_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                       const double* x, double* y, void* stream) {
+  return launch_spmv(indptr, indices, vals, x, y, n, nnz, (cudaStream_t)stream);
+}
+
+int pb200_csr_spmm_f32(const int* indptr, const int* indices, const double* vals, long long n, const float* x,
+                       long long ldx, float* y, long long ldy, int g, void* stream) {
+  csr_spmm_f32_kernel<<<div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, vals, x, y, n, g, ldx, ldy);
+  PB_CHECK_LAUNCH("csr_spmm_f32_kernel");
+  return 0;
+}
+
+int pb200_vec_mul(const double* a, const double* b, double* out, long long n, void* stream) {
+  vec_mul_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+  PB_CHECK_LAUNCH("vec_mul_kernel");
+  return 0;
+}
+
+// V[0] = w / |w|.   scratch: partial[div_up(n,2048)], tmp[1]
+int pb200_lanczos_init(const double* w, long long n, double* V0, double* partial, double* tmp, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = nrm2_into(w, n, partial, tmp, st);
+  if (rc) return rc;
+  scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V0, n, nullptr);
+  PB_CHECK_LAUNCH("scale_by_norm_kernel");
+  return 0;
+}
+
+// Runs Lanczos steps j = j0 .. j0+nsteps-1 on the symmetric CSR matrix.
+// In: V[0..j0] (rows of length ldv >= n) orthonormal.  Out: alpha[j], beta[j+1], V[j+1].
+// Scratch: w[n], h[mcap], partial[mcap * div_up(n,2048)], tmp[1].
+int pb200_lanczos_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                        double* V, long long ldv, int j0, int nsteps, double* alpha, double* beta, double* w,
+                        double* h, double* partial, double* tmp, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = div_up(n, VCHUNK);
+  for (int j = j0; j < j0 + nsteps; ++j) {
+    const int m = j + 1;
+    int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st);
+    if (rc) return rc;
+    // CGS2 against V[0..j]; alpha_j = (first + second) projection on v_j
+    PB_CHECK(cudaMemsetAsync(alpha + j, 0, sizeof(double), st));
+    for (int pass = 0; pass < 2; ++pass) {
+      multi_dot_kernel<<<nblk, VB, 0, st>>>(V, ldv, m, w, n, partial);
+      PB_CHECK_LAUNCH("multi_dot_kernel");
+      reduce_partials_kernel<<<m, 256, 0, st>>>(partial, nblk, m, h, nullptr);
+      PB_CHECK_LAUNCH("reduce_partials_kernel");
+      // alpha_j += h[j]
+      reduce_partials_kernel<<<1, 32, 0, st>>>(h + j, 1, 1, tmp, alpha + j);
+      PB_CHECK_LAUNCH("reduce_partials_kernel(alpha)");
+      multi_axpy_kernel<<<nblk, VB, sizeof(double) * m, st>>>(V, ldv, m, h, w, n);
+      PB_CHECK_LAUNCH("multi_axpy_kernel");
+    }
+    rc = nrm2_into(w, n, partial, tmp, st);
+    if (rc) return rc;
+    scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V + (long long)(j + 1) * ldv, n, beta + j + 1);
+    PB_CHECK_LAUNCH("scale_by_norm_kernel");
+  }
+  return 0;
+}
+
+// U[n][kk] = diag(scale) * V[0..m-1]^T-combination with Y (m x kk, row-major, device).
+int pb200_ritz_vectors(const double* V, long long ldv, int m, const double* Y, int kk, const double* scale,
+                       double* U, long long n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kk < 1 || kk > 32) { set_error_msg("pb200_ritz_vectors: need 1 <= kk <= 32"); return -1; }
+  const size_t smem = sizeof(double) * (size_t)m * kk;
+  if (smem > 200 * 1024) { set_error_msg("pb200_ritz_vectors: m*kk too large for shared memory"); return -1; }
+  if (kk <= 16) {
+    PB_CHECK(cudaFuncSetAttribute(ritz_combine_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ritz_combine_kernel<16><<<div_up(n, 256), 256, smem, st>>>(V, ldv, m, Y, scale, U, n, kk);
+  } else {
+    PB_CHECK(cudaFuncSetAttribute(ritz_combine_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ritz_combine_kernel<32><<<div_up(n, 256), 256, smem, st>>>(V, ldv, m, Y, scale, U, n, kk);
+  }
+  PB_CHECK_LAUNCH("ritz_combine_kernel");
+  return 0;
+}
+
+// A[n][kk] columns scaled to unit L2 norm.  scratch: partial[kk * div_up(n,4096)], sumsq[kk]
+int pb200_normalize_columns(double* A, long long n, int kk, double* partial, double* sumsq, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kk < 1 || kk > 32) { set_error_msg("pb200_normalize_columns: need 1 <= kk <= 32"); return -1; }
+  const int nblk = div_up(n, 4096);
+  col_sumsq_kernel<<<nblk, 256, 0, st>>>(A, n, kk, partial);
+  PB_CHECK_LAUNCH("col_sumsq_kernel");
+  reduce_partials_kernel<<<kk, 256, 0, st>>>(partial, nblk, kk, sumsq, nullptr);
+  PB_CHECK_LAUNCH("reduce_partials_kernel(cols)");
+  col_scale_kernel<<<div_up(n * kk, 256), 256, 0, st>>>(A, n, kk, sumsq);
+  PB_CHECK_LAUNCH("col_scale_kernel");
+  return 0;
+}
+
+}  // extern "C"
