@@ -31,17 +31,19 @@ int pb200_device_sync(void);
 
 /* ---- exact kNN in PCA space: sklearn NearestNeighbors(brute).kneighbors, utils.py:404-407 ---- */
 
-/* Column means, centred FP32 k-major copy xt[d_pad][ld], FP32 score norms yn[ld] (+inf on padding),
- * FP64 centred norms xcn[n], FP64 row norms of the original data xn64[n], max centred norm^2 rmax2[1].
- * d <= 1024, d_pad % 16 == 0, ld % 256 == 0.  col_sums: d doubles of scratch. */
+/* Column means, centred FP32 copy xt[d_pad * ld] in the tiled k-major layout the candidate kernel
+ * streams (point i = 128*tile + il, coordinate c = 16*kc + k at ((tile*(d_pad/16) + kc)*16 + k)*128 + il),
+ * FP32 score norms yn[ld] (+inf on padding), FP64 centred norms xcn[n], FP64 row norms of the original
+ * data xn64[n], max centred norm^2 rmax2[1].
+ * d <= 1024, d_pad % 16 == 0, d_pad - d < 16, ld % 256 == 0.  col_sums: d doubles of scratch. */
 int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, long long ld, double* col_sums,
                       float* xt, float* yn, double* xcn, double* xn64, double* rmax2, void* stream);
 
-/* FP32 candidate generation: for query columns q0..q0+nq-1 of xtq keep the k_keep (<= 48) smallest
- * scores |y|^2 - 2 x.y over all n_ref_pad references.  out_idx/out_score [nq][k_keep] ascending,
+/* FP32 candidate generation: for query points q0..q0+nq-1 of xtq (q0 % 256 == 0) keep the k_keep (<= 48)
+ * smallest scores |y|^2 - 2 x.y over all n_ref_pad references.  out_idx/out_score [nq][k_keep] ascending,
  * out_thr[nq] = k_keep-th score (lower bound for every excluded reference; +inf if nothing excluded). */
-int pb200_knn_candidates_f32(const float* xtq, long long ldq, const float* xtr, long long ldr, const float* yn,
-                             int q0, int nq, long long n_ref_pad, int d_pad, int k_keep, int* out_idx,
+int pb200_knn_candidates_f32(const float* xtq, long long nq_pad, const float* xtr, long long n_ref_pad,
+                             const float* yn, int q0, int nq, int d, int d_pad, int k_keep, int* out_idx,
                              float* out_score, float* out_thr, void* stream);
 
 /* FP64 re-rank with the reference's expanded-form distance; out_idx/out_dist [nq][k] ascending by
@@ -107,6 +109,51 @@ int pb200_ritz_vectors(const double* V, long long ldv, int m, const double* Y, i
                        double* U, long long n, void* stream);
 /* unit-L2 columns.  scratch: partial[kk * (n/4096+1)], sumsq[kk] */
 int pb200_normalize_columns(double* A, long long n, int kk, double* partial, double* sumsq, void* stream);
+
+/* ---- run_palantir: scaling, boundaries, waypoint sampling (core.py:176-186, 252-312) ---- */
+/* scratch: pval[2*m*nblk] doubles, pidx[2*m*nblk] long long, nblk = min(1024, ceil(n/256)) */
+int pb200_col_minmax(const double* a, long long n, int m, double* omin, long long* oimin, double* omax,
+                     long long* oimax, double* pval, long long* pidx, void* stream);
+int pb200_minmax_apply(const double* a, long long n, int m, const double* mn, const double* mx, double* out,
+                       void* stream);
+/* out[m][iters]; scratch: vt[m*n], md[m*n], cur[m], pv[m*592], pi[m*592], done[m] */
+int pb200_maxmin_sampling(const double* data, long long n, int m, const long long* first, int iters,
+                          long long* out, double* vt, double* md, long long* cur, double* pv, long long* pi,
+                          unsigned int* done, void* stream);
+int pb200_gather_rows_f64(const double* a, int m, const long long* rows, long long nr, double* out, void* stream);
+
+/* ---- reachability (networkx pass of _connect_graph, core.py:806-817) ---- */
+int pb200_graph_components(const int* indptr, const int* indices, long long n, int* label, void* stream);
+int pb200_count_other_label(const int* label, long long n, long long ref, int* count, void* stream);
+int pb200_point_dists_expanded(const double* data, long long n, int m, long long p, double* out, void* stream);
+
+/* ---- multi-source shortest paths: scipy.sparse.csgraph.dijkstra(directed=False), core.py:362 ---- */
+int pb200_sssp_num_ctas(int n_sources);
+/* D[n_sources][n]; scratch: q[n_ctas*3*n] int, bits[n_ctas*2*ceil(n/32)] uint32; stats [n_sources][3] or NULL */
+int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
+                     int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,
+                     void* stream);
+
+/* ---- pseudotime refinement and projection (core.py:368-397, 225-230) ---- */
+int pb200_sum_pow_f64(const double* x, long long count, double shift, int power, double* partial, double* out,
+                      void* stream);
+int pb200_waypoint_colsum(const double* D, int S, long long n, double sdv, double* colsum, void* stream);
+int pb200_refine_step(const double* D, int S, long long n, double sdv, const double* colsum, const double* pt,
+                      const double* t_mask, const double* t_add, int plus_row, double* out, void* stream);
+int pb200_project_fates(const double* D, int S, long long n, double sdv, const double* colsum, const double* B,
+                        int nt, double* fates, void* stream);
+int pb200_row_entropy(const double* fates, long long n, int nt, double* ent, void* stream);
+int pb200_pearson_sums(const double* x, const double* y, long long n, double mx, double my, double* partial,
+                       double* out, void* stream);
+int pb200_shift_scale(double* x, long long n, double sub, double div, void* stream);
+
+/* ---- waypoint Markov chain and absorption solve (core.py:523-563, 699-737) ---- */
+int pb200_markov_chain_dense(const int* ind, const double* dist, int S, int knn, int ka, const double* pt,
+                             double* aff, double* rowsum, double* T, void* stream);
+int pb200_absorb_system(const double* T, int S, const int* trans, int nt, const int* absn, int na, double* A,
+                        double* R, void* stream);
+int pb200_dense_solve_f64(double* A, double* B, int n, int r, int* singular, void* stream);
+int pb200_dense_matvec_t(const double* M, int S, const double* x, double* y, void* stream);
 
 #ifdef __cplusplus
 }

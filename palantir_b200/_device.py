@@ -93,7 +93,7 @@ def sklearn_uses_brute(n: int, d: int, n_neighbors: int) -> bool:
 @dataclass
 class KnnPrep:
     x: torch.Tensor          # original data [n, d] f32/f64
-    xt: torch.Tensor         # centred FP32 k-major copy [d_pad, ld]
+    xt: torch.Tensor         # centred FP32 copy, tiled k-major (d_pad * ld floats)
     yn: torch.Tensor
     xcn: torch.Tensor
     xn64: torch.Tensor
@@ -145,7 +145,7 @@ def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
     score = empty((nq, k_keep), F32)
     thr = empty((nq,), F32)
     with stage("knn_candidates"):
-        call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.xt, prep.ld, prep.yn, q0, nq, prep.ld,
+        call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.xt, prep.ld, prep.yn, q0, nq, prep.d,
              prep.d_pad, k_keep, cand, score, thr)
     flag = empty((nq,), U8)
     n_flagged = empty((1,), I32)

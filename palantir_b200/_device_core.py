@@ -1,0 +1,303 @@
+"""Device-side orchestration of the run_palantir stages (scaling, waypoint sampling,
+kNN graph, reachability, multi-source shortest paths, refinement, Markov chain,
+absorption solve, projection).  CUDA tensors in, CUDA tensors out; see core.py for
+the host mirror of the reference API.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _device as dv
+from . import _dist, _native
+from ._device import F64, I32, I64, call, empty, stage, zeros
+
+U32 = torch.int32  # bitmaps / counters are passed as raw 32-bit words
+
+
+# ---------------------------------------------------------------------------
+# scaling, boundaries, sampling
+# ---------------------------------------------------------------------------
+def col_minmax(a: torch.Tensor):
+    """(min, argmin, max, argmax) per column, first occurrence on ties."""
+    n, m = a.shape
+    nblk = min(1024, (n + 255) // 256)
+    omin, omax = empty((m,), F64), empty((m,), F64)
+    oimin, oimax = empty((m,), I64), empty((m,), I64)
+    pval = empty((2 * m * nblk,), F64)
+    pidx = empty((2 * m * nblk,), I64)
+    call("pb200_col_minmax", a, n, m, omin, oimin, omax, oimax, pval, pidx)
+    return omin, oimin, omax, oimax
+
+
+def minmax_scale(ms: torch.Tensor) -> torch.Tensor:
+    n, m = ms.shape
+    mn, _, mx, _ = col_minmax(ms)
+    out = empty((n, m), F64)
+    call("pb200_minmax_apply", ms, n, m, mn, mx, out)
+    return out
+
+
+def maxmin_sampling(data: torch.Tensor, first: np.ndarray, iters: int) -> np.ndarray:
+    """[m, iters] waypoint positions: column c starts at first[c] (drawn on the host with
+    the reference's RNG calls) and adds iters-1 farthest points."""
+    n, m = data.shape
+    nblk = min(592, (n + 255) // 256)
+    out = empty((m, iters), I64)
+    vt = empty((m * n,), F64)
+    md = empty((m * n,), F64)
+    cur = empty((m,), I64)
+    pv = empty((m * nblk,), F64)
+    pi = empty((m * nblk,), I64)
+    done = empty((m,), I32)
+    with stage("maxmin_sampling"):
+        call("pb200_maxmin_sampling", data, n, m, dv.to_device(first.astype(np.int64)), iters, out, vt, md, cur,
+             pv, pi, done)
+    return out.cpu().numpy()
+
+
+def gather_rows(a: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    m = 1 if a.dim() == 1 else a.shape[1]
+    out = empty((rows.numel(),) if a.dim() == 1 else (rows.numel(), m), F64)
+    call("pb200_gather_rows_f64", a, m, rows, rows.numel(), out)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# kNN graph, reachability, shortest paths
+# ---------------------------------------------------------------------------
+def knn_table(data: torch.Tensor, knn: int):
+    """Self-including neighbour table of all cells in the (low-dimensional) multiscale
+    space, rows sharded across ranks."""
+    n = data.shape[0]
+    if knn > n:
+        raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {knn}, n_samples_fit = {n}")
+    q0, nq = _dist.row_shard(n, 256)
+    idx, dist, stats = dv.knn_like_sklearn(data, knn, q0, nq)
+    idx, dist = _dist.allgather_rows(idx, dist, n, 256)
+    return idx, dist, stats
+
+
+def undirected_graph(idx: torch.Tensor, dist: torch.Tensor) -> dv.DeviceCSR:
+    """Symmetric CSR with min(w_ij, w_ji) on the union pattern, self loops dropped: the graph
+    csgraph.dijkstra(directed=False) effectively walks (core.py:362)."""
+    with stage("graph_build"):
+        return dv.symmetrize(idx, dist.contiguous(), 0, 1, True)
+
+
+def unreachable_count(g: dv.DeviceCSR, start: int):
+    label = empty((g.n,), I32)
+    count = empty((1,), I32)
+    call("pb200_graph_components", g.indptr, g.indices, g.n, label)
+    call("pb200_count_other_label", label, g.n, start, count)
+    return int(count.item()), label
+
+
+def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, want_stats: bool = False):
+    """D[S, n] shortest-path distances from each source (unreachable = +inf)."""
+    n, S = g.n, int(sources.numel())
+    if delta is None:
+        delta = 4.0 * float(g.data.mean().item()) if g.nnz else 1.0
+        if not (delta > 0.0):
+            delta = 1.0
+    D = empty((S, n), F64)
+    lib = _native.load()
+    n_ctas = lib.pb200_sssp_num_ctas(S)
+    q = empty((n_ctas * 3 * n,), I32)
+    bits = empty((n_ctas * 2 * ((n + 31) // 32),), U32)
+    stats = zeros((S, 3), I64) if want_stats else None
+    with stage("sssp"):
+        call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, bits, stats)
+    return D, stats
+
+
+def connect_graph(idx: torch.Tensor, dist: torch.Tensor, data: torch.Tensor, start: int):
+    """core.py:806-842 on the device.  Returns the undirected graph; when some cells are
+    unreachable from `start` the reference's loop is followed literally: farthest reachable
+    cell -> its nearest (sklearn euclidean) unreachable cell, one arc per iteration."""
+    g = undirected_graph(idx, dist)
+    n_unreach, label = unreachable_count(g, start)
+    if n_unreach == 0:
+        return g
+    warnings.warn(
+        "Some of the cells were unreachable. Consider increasing the k for \n \
+            nearest neighbor graph construction.")
+    n = g.n
+    src = torch.tensor([start], dtype=I64, device=idx.device)
+    pd = empty((n,), F64)
+    while n_unreach > 0:
+        D, _ = sssp(g, src)
+        d0 = D[0]
+        reach = torch.isfinite(d0)
+        far = int(torch.argmax(torch.where(reach, d0, torch.full_like(d0, -1.0))).item())
+        call("pb200_point_dists_expanded", data, n, data.shape[1], far, pd)
+        cand = torch.where(reach, torch.full_like(pd, float("inf")), pd)
+        j = int(torch.argmin(cand).item())
+        w = pd[j:j + 1]
+        # widen the arc table by one column: self everywhere (dropped) except far -> j
+        extra_i = torch.arange(n, dtype=I32, device=idx.device).unsqueeze(1)
+        extra_d = zeros((n, 1), F64)
+        extra_i[far, 0] = j
+        extra_d[far, 0] = w[0]
+        idx = torch.cat([idx, extra_i], dim=1).contiguous()
+        dist = torch.cat([dist, extra_d], dim=1).contiguous()
+        g = undirected_graph(idx, dist)
+        n_unreach, label = unreachable_count(g, start)
+    return g
+
+
+# ---------------------------------------------------------------------------
+# refinement
+# ---------------------------------------------------------------------------
+def _sum_pow(x: torch.Tensor, shift: float, power: int) -> float:
+    cnt = x.numel()
+    partial = empty((cnt // 4096 + 2,), F64)
+    out = empty((1,), F64)
+    call("pb200_sum_pow_f64", x, cnt, float(shift), power, partial, out)
+    return out
+
+
+def bandwidth(D: torch.Tensor, total_count: int) -> float:
+    """sdv = std(D) * 1.06 * count^(-1/5) (core.py:368); D may be this rank's row shard."""
+    s1 = _dist.allreduce_sum_(_sum_pow(D, 0.0, 1))
+    mean = float(s1.item()) / total_count
+    s2 = _dist.allreduce_sum_(_sum_pow(D, mean, 2))
+    std = math.sqrt(float(s2.item()) / total_count)
+    return std * 1.06 * total_count ** (-1 / 5)
+
+
+def pearson(x: torch.Tensor, y: torch.Tensor) -> float:
+    n = x.numel()
+    partial = empty((3 * (n // 4096 + 2),), F64)
+    out = empty((3,), F64)
+    mx = float(_sum_pow(x, 0.0, 1).item()) / n
+    my = float(_sum_pow(y, 0.0, 1).item()) / n
+    call("pb200_pearson_sums", x, y, n, mx, my, partial, out)
+    sxy, sxx, syy = out.cpu().tolist()
+    return sxy / math.sqrt(sxx * syy)
+
+
+def refine_pseudotime(D: torch.Tensor, row0: int, n_rows_total: int, wp_cells: torch.Tensor, start_row: int,
+                      max_iterations: int, verbose: bool = True):
+    """core.py:368-397.  D holds waypoint rows row0..row0+S-1 of the full nW x N matrix
+    (all of it on one GPU).  Returns (pseudotime[N] in [0,1], colsum[N], sdv)."""
+    S, n = D.shape
+    sdv = bandwidth(D, n_rows_total * n)
+    colsum = empty((n,), F64)
+    with stage("refine"):
+        call("pb200_waypoint_colsum", D, S, n, sdv, colsum)
+        _dist.allreduce_sum_(colsum)
+        # initial pseudotime = distance row of the start waypoint
+        if row0 <= start_row < row0 + S:
+            pt = D[start_row - row0].clone()
+        else:
+            pt = zeros((n,), F64)
+        _dist.allreduce_sum_(pt) if _dist.world()[1] > 1 else None
+        plus_row = start_row - row0 if row0 <= start_row < row0 + S else -1
+        my_cells = wp_cells[row0:row0 + S].contiguous()
+        it, converged = 1, False
+        while not converged and it < max_iterations:
+            t_mask = gather_rows(pt, my_cells)
+            t_add = t_mask.clone()
+            if plus_row >= 0:
+                t_add[plus_row] = 0.0
+            new = empty((n,), F64)
+            call("pb200_refine_step", D, S, n, sdv, colsum, pt, t_mask, t_add, plus_row, new)
+            _dist.allreduce_sum_(new)
+            corr = pearson(pt, new)
+            if verbose:
+                print("Correlation at iteration %d: %.4f" % (it, corr))
+            converged = corr > 0.9999
+            pt = new
+            it += 1
+        mn, _, mx, _ = col_minmax(pt.view(n, 1))
+        lo, hi = float(mn.item()), float(mx.item())
+        call("pb200_shift_scale", pt, n, lo, hi - lo)
+    return pt, colsum, sdv
+
+
+def project_fates(D: torch.Tensor, sdv: float, colsum: torch.Tensor, B: torch.Tensor):
+    """fates[N, nT] = W_norm^T B and the per-cell entropy (core.py:225-230)."""
+    S, n = D.shape
+    nt = B.shape[1]
+    fates = zeros((n, nt), F64)
+    ent = empty((n,), F64)
+    with stage("project"):
+        if nt > 0:
+            call("pb200_project_fates", D, S, n, sdv, colsum, B.contiguous(), nt, fates)
+            _dist.allreduce_sum_(fates)
+        call("pb200_row_entropy", fates, n, nt, ent)
+    return fates, ent
+
+
+# ---------------------------------------------------------------------------
+# Markov chain on the waypoints and absorption probabilities
+# ---------------------------------------------------------------------------
+def markov_chain_dense(wp_data: torch.Tensor, knn: int, pt_wp: torch.Tensor) -> torch.Tensor:
+    """Dense row-stochastic T[S, S] of core.py:523-563."""
+    S = wp_data.shape[0]
+    if knn > S:
+        raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {knn}, n_samples_fit = {S}")
+    ind, dist, _ = dv.knn_like_sklearn(wp_data.contiguous(), knn)
+    ka = int(min(int(math.floor(knn / 3)) - 1, 30))
+    if ka < 0:
+        ka += knn                      # numpy's negative index (knn < 3)
+    T = zeros((S, S), F64)
+    aff = empty((S * knn,), F64)
+    rowsum = empty((S,), F64)
+    with stage("markov_chain"):
+        call("pb200_markov_chain_dense", ind, dist, S, knn, ka, pt_wp.contiguous(), aff, rowsum, T)
+    return T
+
+
+def absorption_probabilities(T: torch.Tensor, abs_states: np.ndarray):
+    """core.py:699-765: B[S, nA] in waypoint order (transient rows solved, absorbing rows = identity)."""
+    S = T.shape[0]
+    abs_states = np.asarray(abs_states, dtype=np.int64)
+    trans = np.setdiff1d(np.arange(S), abs_states)
+    na, nt = len(abs_states), len(trans)
+    B = zeros((S, na), F64)
+    if na == 0:
+        return B
+    abs_d = dv.to_device(abs_states.astype(np.int32))
+    B[torch.from_numpy(abs_states).to(B.device), torch.arange(na, device=B.device)] = 1.0
+    if nt == 0:
+        return B
+    trans_d = dv.to_device(trans.astype(np.int32))
+    A = empty((nt, nt), F64)
+    R = empty((nt, na), F64)
+    singular = empty((1,), I32)
+    with stage("absorption_solve"):
+        call("pb200_absorb_system", T, S, trans_d, nt, abs_d, na, A, R)
+        call("pb200_dense_solve_f64", A, R, nt, na, singular)
+    if int(singular.item()) != 0:
+        raise RuntimeError("absorption system (I - Q) is singular")
+    R.clamp_(min=0.0)                       # core.py:753
+    B[torch.from_numpy(trans).to(B.device)] = R
+    return B
+
+
+def stationary_ranks(T: torch.Tensor, iters: int = 20000, tol: float = 1e-13) -> np.ndarray:
+    """|leading left eigenvector| of T (core.py:599-600) by power iteration on the device,
+    started from the uniform vector (the reference lets ARPACK pick a random start)."""
+    S = T.shape[0]
+    x = torch.full((S,), 1.0 / S, dtype=F64, device=T.device)
+    y = empty((S,), F64)
+    for it in range(iters):
+        call("pb200_dense_matvec_t", T, S, x, y)
+        nrm = float(_sum_pow(y, 0.0, 2).item()) ** 0.5
+        if nrm == 0.0:
+            break
+        call("pb200_shift_scale", y, S, 0.0, nrm)
+        if it % 50 == 49:
+            diff = float(_sum_pow(y - x, 0.0, 2).item()) ** 0.5
+            x, y = y, x
+            if diff < tol:
+                break
+        else:
+            x, y = y, x
+    return np.abs(x.cpu().numpy())

@@ -11,15 +11,19 @@
 // k, and proves with an FP32 error bound that no excluded point can belong to the
 // true top-k (rows that cannot be proven are redone exactly in FP64).
 //
-// Layout: coordinates are stored k-major ("XT"): XT[c * ld + i] is coordinate c
-// of point i, ld a multiple of 256, d padded with zero rows to a multiple of 16.
-// A CTA owns 256 query rows and streams every 128-point reference tile through a
-// 3-stage shared-memory ring filled by the TMA engine (cp.async.bulk, one elected
-// thread, mbarrier full/empty pairs).  16 consumer warps each own 16
+// Layout: coordinates are stored tiled and k-major ("XT"): point i = 128*tile + il,
+// coordinate c = 16*kc + k lives at XT[((tile*KCH + kc)*16 + k)*128 + il], so the
+// 16 x 128 operand block of one (tile, kc) pipeline chunk is 8 KB of contiguous
+// memory and moves with ONE bulk copy; the last chunk of a tile carries only
+// k_tail = round_up(d - 16 (KCH-1), 4) coordinate rows.  The point count is padded
+// to a multiple of 256.  A CTA owns 256 query rows and streams every 128-point
+// reference tile through a 3-stage shared-memory ring filled by the TMA engine
+// (cp.async.bulk + mbarrier full/empty pairs; whichever warp reaches a chunk first
+// issues the copies for the chunk two ahead, so no warp waits on a fixed producer).  16 consumer warps each own 16
 // query rows x 128 reference columns (8x8 register micro-tile per thread), so the
 // top-K lists of a row are only ever touched by one warp and the selection needs
-// no CTA-wide barrier.  One CTA per SM (512 threads, <=128 registers); lane 0 of
-// warp 0 doubles as the TMA producer (a 17th warp would cap registers at 96).
+// no CTA-wide barrier.  One CTA per SM (512 threads, <=128 registers; a 17th,
+// dedicated producer warp would cap registers at 96).
 #include "common.cuh"
 
 namespace pb200 {
@@ -35,11 +39,11 @@ constexpr int KNN_CONSUMER_WARPS = 16;
 constexpr int KNN_THREADS = KNN_CONSUMER_WARPS * 32;
 
 struct KnnStage {
-  float a[KNN_DK][KNN_BM];
+  float a[2][KNN_DK][KNN_BN];  // two 128-row query tiles
   float b[KNN_DK][KNN_BN];
   float yn[KNN_BN];
 };
-constexpr uint32_t KNN_STAGE_TX = KNN_DK * KNN_BM * 4 + KNN_DK * KNN_BN * 4;
+constexpr int KNN_BLOCK_FLOATS = KNN_DK * KNN_BN;  // one (tile, kc) operand block
 
 struct KnnSmem {
   KnnStage st[KNN_NST];
@@ -48,18 +52,18 @@ struct KnnSmem {
   float thr[KNN_BM];
   uint64_t full[KNN_NST];
   uint64_t empty[KNN_NST];
+  int next_chunk;  // next pipeline chunk nobody has issued yet
 };
 
 struct KnnParams {
-  const float* xtq;  // query coordinates, k-major
-  long long ldq;
-  const float* xtr;  // reference coordinates, k-major
-  long long ldr;
+  const float* xtq;  // query coordinates, tiled k-major
+  const float* xtr;  // reference coordinates, tiled k-major
   const float* yn;   // |y_j|^2 per reference (FP32, +inf on padding)
-  int q0;            // first query column in xtq (multiple of 256)
+  int q0;            // first query point (multiple of 256)
   int nq;            // number of query rows handled by this launch
-  int n_ref_tiles;   // ldr-padded reference count / 128
+  int n_ref_tiles;   // padded reference count / 128
   int kch;           // d_pad / 16
+  int k_tail;        // coordinate rows in the last chunk of a tile (multiple of 4, <= 16)
   int k_keep;
   int* out_idx;      // [nq][k_keep]
   float* out_score;  // [nq][k_keep]
@@ -121,37 +125,39 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
   const int T = p.n_ref_tiles;
   const int KCH = p.kch;
 
-  // ---------------- producer state (warp 0, lane 0 drives the TMA engine) -------------
-  // The producer runs KNN_NST-1 chunks ahead of warp 0's own consumption; before
-  // refilling a stage it waits on that stage's "empty" barrier (all 16 warps done).
-  const bool is_producer = (tid == 0);
-  int p_t = 0, p_kc = 0, p_stage = 0;
-  uint32_t p_phase = 0;
-  auto produce = [&]() {
-    if (p_t >= T) return;
-    mbar_wait(&sm.empty[p_stage], p_phase ^ 1u);
-    const bool last = (p_kc == KCH - 1);
-    mbar_arrive_expect_tx(&sm.full[p_stage], KNN_STAGE_TX + (last ? KNN_BN * 4u : 0u));
-    const float* aq = p.xtq + (long long)(p_kc * KNN_DK) * p.ldq + qbase;
-    const float* br = p.xtr + (long long)(p_kc * KNN_DK) * p.ldr + (long long)p_t * KNN_BN;
-#pragma unroll
-    for (int k = 0; k < KNN_DK; ++k)
-      bulk_g2s(&sm.st[p_stage].a[k][0], aq + (long long)k * p.ldq, KNN_BM * 4, &sm.full[p_stage]);
-#pragma unroll
-    for (int k = 0; k < KNN_DK; ++k)
-      bulk_g2s(&sm.st[p_stage].b[k][0], br + (long long)k * p.ldr, KNN_BN * 4, &sm.full[p_stage]);
-    if (last) bulk_g2s(&sm.st[p_stage].yn[0], p.yn + (long long)p_t * KNN_BN, KNN_BN * 4, &sm.full[p_stage]);
-    if (++p_stage == KNN_NST) { p_stage = 0; p_phase ^= 1u; }
-    if (++p_kc == KCH) { p_kc = 0; ++p_t; }
+  // ---------------- producer: issued by whichever warp gets there first ---------------
+  // Chunk g = t*KCH + kc lives in stage g % NST.  Before refilling a stage the issuing
+  // thread waits on its "empty" barrier (all 16 warps done with the previous tenant).
+  const int total_chunks = T * KCH;
+  const int qtile0 = qbase / KNN_BN;
+  auto produce = [&](int g) {
+    const int t = g / KCH, kc = g - t * KCH;
+    const int st = g % KNN_NST;
+    const uint32_t ph = (uint32_t)(g / KNN_NST) & 1u;
+    mbar_wait(&sm.empty[st], ph ^ 1u);
+    const bool last = (kc == KCH - 1);
+    const uint32_t blk_bytes = (uint32_t)(last ? p.k_tail : KNN_DK) * KNN_BN * 4u;
+    mbar_arrive_expect_tx(&sm.full[st], 3u * blk_bytes + (last ? KNN_BN * 4u : 0u));
+    const float* a0 = p.xtq + ((long long)qtile0 * KCH + kc) * KNN_BLOCK_FLOATS;
+    const float* a1 = a0 + (long long)KCH * KNN_BLOCK_FLOATS;
+    const float* br = p.xtr + ((long long)t * KCH + kc) * KNN_BLOCK_FLOATS;
+    bulk_g2s(&sm.st[st].a[0][0][0], a0, blk_bytes, &sm.full[st]);
+    bulk_g2s(&sm.st[st].a[1][0][0], a1, blk_bytes, &sm.full[st]);
+    bulk_g2s(&sm.st[st].b[0][0], br, blk_bytes, &sm.full[st]);
+    if (last) bulk_g2s(&sm.st[st].yn[0], p.yn + (long long)t * KNN_BN, KNN_BN * 4, &sm.full[st]);
   };
-  if (is_producer) {
-    for (int s = 0; s < KNN_NST - 1; ++s) produce();
+  if (tid == 0) {
+    int g = 0;
+    for (; g < KNN_NST - 1 && g < total_chunks; ++g) produce(g);
+    sm.next_chunk = g;
   }
+  __syncthreads();
 
   // ---------------- consumers ---------------------------------------------------------
   const int r0 = warp * 16 + (lane >> 4) * 8;  // first of this thread's 8 rows (CTA-local)
+  const int a_off = (r0 >> 7) * KNN_BLOCK_FLOATS + (r0 & 127);
   const int c0 = (lane & 15) * 4;              // columns c0..c0+3 and 64+c0..64+c0+3
-  int stage = 0;
+  int stage = 0, gchunk = 0;
   uint32_t phase = 0;
   float acc[8][8];
   float ynr[8];
@@ -162,23 +168,45 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-    for (int kc = 0; kc < KCH; ++kc) {
-      if (is_producer) produce();
+    for (int kc = 0; kc < KCH; ++kc, ++gchunk) {
+      if (lane == 0) {
+        const int target = gchunk + KNN_NST - 1;
+        if (target < total_chunks && *(volatile int*)&sm.next_chunk == target &&
+            atomicCAS(&sm.next_chunk, target, target + 1) == target)
+          produce(target);
+      }
       mbar_wait(&sm.full[stage], phase);
-      const float* As = &sm.st[stage].a[0][0];
-      const float* Bs = &sm.st[stage].b[0][0];
+      const float* As = &sm.st[stage].a[0][0][0] + a_off;
+      const float* Bs = &sm.st[stage].b[0][0] + c0;
+      if (kc < KCH - 1 || p.k_tail == KNN_DK) {
 #pragma unroll
-      for (int k = 0; k < KNN_DK; ++k) {
-        const float4 a0 = *reinterpret_cast<const float4*>(As + k * KNN_BM + r0);
-        const float4 a1 = *reinterpret_cast<const float4*>(As + k * KNN_BM + r0 + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN + c0);
-        const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN + 64 + c0);
-        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        for (int k = 0; k < KNN_DK; ++k) {
+          const float4 a0 = *reinterpret_cast<const float4*>(As + k * KNN_BN);
+          const float4 a1 = *reinterpret_cast<const float4*>(As + k * KNN_BN + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN);
+          const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN + 64);
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+      } else {
+        const int kt = p.k_tail;
+#pragma unroll 4
+        for (int k = 0; k < kt; ++k) {
+          const float4 a0 = *reinterpret_cast<const float4*>(As + k * KNN_BN);
+          const float4 a1 = *reinterpret_cast<const float4*>(As + k * KNN_BN + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN);
+          const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN + 64);
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
       }
       if (kc == KCH - 1) {
         const float4 y0 = *reinterpret_cast<const float4*>(&sm.st[stage].yn[c0]);
@@ -296,7 +324,8 @@ __global__ void col_sums_kernel(const T* __restrict__ x, long long n, int d, dou
   }
 }
 
-// One block = 32 points.  Writes xt[c*ld + i] = (float)(x[i][c] - mean[c]) (0 on
+// One block = 32 points.  Writes the tiled k-major copy (see the header comment)
+// xt[((i/128 * KCH + c/16)*16 + c%16)*128 + i%128] = (float)(x[i][c] - mean[c]) (0 on
 // padding), yn[i] = (float)sum_c xt^2 (+inf on padding rows), xcn[i] = the same
 // sum in FP64, xn64[i] = sum_c x[i][c]^2 in FP64 on the ORIGINAL values (the
 // reference's row norm), and the running max of xcn in *rmax2_bits.
@@ -332,7 +361,11 @@ __global__ void knn_prep_kernel(const T* __restrict__ x, long long n, int d, int
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       const int c = cb + ty + 8 * rr;
-      if (c < d_pad) xt[(long long)c * ld + i0 + tx] = tile[tx][ty + 8 * rr];
+      if (c < d_pad) {
+        const long long i = i0 + tx;
+        const long long kch = d_pad / KNN_DK;
+        xt[(((i >> 7) * kch + (c >> 4)) * KNN_DK + (c & 15)) * KNN_BN + (i & 127)] = tile[tx][ty + 8 * rr];
+      }
     }
     __syncthreads();
   }
@@ -407,24 +440,26 @@ int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, 
   return 0;
 }
 
-int pb200_knn_candidates_f32(const float* xtq, long long ldq, const float* xtr, long long ldr, const float* yn,
-                             int q0, int nq, long long n_ref_pad, int d_pad, int k_keep, int* out_idx,
+int pb200_knn_candidates_f32(const float* xtq, long long nq_pad, const float* xtr, long long n_ref_pad,
+                             const float* yn, int q0, int nq, int d, int d_pad, int k_keep, int* out_idx,
                              float* out_score, float* out_thr, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (k_keep < 1 || k_keep > KNN_MAX_KEEP || q0 % KNN_BM != 0 || n_ref_pad % KNN_BN != 0 ||
-      d_pad % KNN_DK != 0 || d_pad < KNN_DK) {
+  if (k_keep < 1 || k_keep > KNN_MAX_KEEP || q0 % KNN_BM != 0 || n_ref_pad % KNN_BM != 0 ||
+      nq_pad % KNN_BM != 0 || d_pad % KNN_DK != 0 || d_pad < KNN_DK || d < 1 || d > d_pad ||
+      d_pad - d >= KNN_DK) {
     set_error_msg("pb200_knn_candidates_f32: bad k_keep / alignment");
     return -1;
   }
   if (nq <= 0) return 0;
   const int tiles = div_up(nq, KNN_BM);
-  if ((long long)q0 + (long long)tiles * KNN_BM > ldq) {
-    set_error_msg("pb200_knn_candidates_f32: query tiles exceed ldq");
+  if ((long long)q0 + (long long)tiles * KNN_BM > nq_pad) {
+    set_error_msg("pb200_knn_candidates_f32: query tiles exceed the padded query count");
     return -1;
   }
   KnnParams p;
-  p.xtq = xtq; p.ldq = ldq; p.xtr = xtr; p.ldr = ldr; p.yn = yn;
+  p.xtq = xtq; p.xtr = xtr; p.yn = yn;
   p.q0 = q0; p.nq = nq; p.n_ref_tiles = (int)(n_ref_pad / KNN_BN); p.kch = d_pad / KNN_DK; p.k_keep = k_keep;
+  p.k_tail = ((d - (d_pad - KNN_DK)) + 3) / 4 * 4;
   p.out_idx = out_idx; p.out_score = out_score; p.out_thr = out_thr;
   static bool attr_set = false;
   const int smem = (int)sizeof(KnnSmem);

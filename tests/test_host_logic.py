@@ -1,0 +1,191 @@
+"""CPU: host-side mirror (validation, config, PResults, multiscale space, sharding, ABI exports)."""
+import os
+import re
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import ROOT, golden
+
+
+def test_library_exports_every_declared_symbol():
+    from palantir_b200 import _native
+
+    decl = _native.parse_header()
+    assert len(decl) >= 40
+    if not os.path.exists(_native.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (pb200_\w+)", out))
+    missing = sorted(set(decl) - exported)
+    assert not missing, missing
+    lib = _native.load()                      # loads and binds every prototype (no compute call)
+    assert lib.pb200_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+
+    from palantir_b200 import _native, utils
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_native.NativeLibraryError):
+        utils.compute_kernel(pd.DataFrame(np.random.rand(40, 20)), backend="sklearn")
+
+
+def test_product_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "palantir_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_multiscale_space_matches_oracle_and_reference_rules():
+    from oracle import palantir_oracle as po
+    from palantir_b200 import utils
+
+    z = golden("dm_f32_n1500_d20.npz")
+    res = {"EigenValues": pd.Series(z["evals_asis"]), "EigenVectors": pd.DataFrame(z["evecs_asis"])}
+    ms = utils.determine_multiscale_space(res)
+    assert isinstance(ms, pd.DataFrame)
+    assert np.array_equal(ms.values, z["ms_asis"])
+    assert utils.determine_multiscale_space(res, n_eigs=3).shape[1] == 2      # reference test :20-22
+    with pytest.raises(ValueError):
+        utils.determine_multiscale_space("not a dict")
+    assert po.pick_n_eigs(z["evals_asis"]) - 1 == ms.shape[1]
+
+
+def test_multiscale_space_anndata_like():
+    from palantir_b200 import utils
+    from palantir_b200.compat import AnnDataLike, is_anndata
+
+    z = golden("dm_f32_n1500_d20.npz")
+    ad = AnnDataLike(np.zeros((1500, 3)))
+    assert is_anndata(ad) and not is_anndata(pd.DataFrame()) and not is_anndata({})
+    ad.obsm["DM_EigenVectors"] = z["evecs_asis"]
+    ad.uns["DM_EigenValues"] = z["evals_asis"]
+    out = utils.determine_multiscale_space(ad)
+    assert np.array_equal(ad.obsm["DM_EigenVectors_multiscaled"], out.values)
+    assert list(out.index) == list(ad.obs_names)
+
+
+def test_input_validation_errors():
+    from palantir_b200 import core, utils
+
+    with pytest.raises(ValueError):
+        utils.run_diffusion_maps("nope")
+    with pytest.raises(ValueError):
+        utils.compute_kernel(pd.DataFrame(np.random.rand(10, 3)), backend="faiss")
+    with pytest.raises(ValueError):
+        utils.run_magic_imputation(np.zeros((3, 3)))
+    df = pd.DataFrame(np.random.rand(20, 4), index=[f"c{i}" for i in range(20)])
+    with pytest.raises(ValueError):
+        core.run_palantir(df, "c0", knn=0)
+    with pytest.raises(ValueError):
+        core.run_palantir(df, "missing_cell")
+
+
+def test_normalize_cell_identifiers():
+    from palantir_b200 import config
+    from palantir_b200.validation import normalize_cell_identifiers as norm
+
+    obs = pd.Index(["1", "2", "3"])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        d, nreq, nfound = norm([1, 2, 9], obs)
+    assert set(d) == {"1", "2", "9"} and (nreq, nfound) == (3, 2) and len(w) >= 1
+    d, nreq, nfound = norm(pd.Series({"1": "A"}), obs)
+    assert d == {"1": "A"} and nfound == 1
+    d, _, nfound = norm(["1"], pd.Index([1, 2, 3]))
+    assert nfound == 1                              # obs_names treated as strings
+    config.AUTO_CONVERT_CELL_IDS_TO_STR = False
+    try:
+        with warnings.catch_warnings(record=True):
+            warnings.simplefilter("always")
+            _, _, nfound = norm([1], obs)
+        assert nfound == 0
+    finally:
+        config.AUTO_CONVERT_CELL_IDS_TO_STR = True
+    with pytest.raises(ValueError):
+        norm(3.5, obs)
+    with pytest.raises(ValueError):
+        norm([], obs)
+
+
+def test_presults_clips_small_probabilities(tmp_path):
+    from palantir_b200.presults import PResults
+
+    bp = pd.DataFrame([[0.005, 0.995], [0.5, 0.5]])
+    pr = PResults(pd.Series([0.0, 1.0]), pd.Series([0.1, 0.7]), bp, pd.Index([0]))
+    assert pr.branch_probs.iloc[0, 0] == 0 and pr.branch_probs.iloc[0, 1] == 0.995
+    f = tmp_path / "r.pkl"
+    pr.save(str(f))
+    assert PResults.load(str(f)).branch_probs.equals(pr.branch_probs)
+
+
+def test_sklearn_auto_rule():
+    from palantir_b200._device import sklearn_uses_brute
+
+    assert sklearn_uses_brute(1000, 16, 31) and not sklearn_uses_brute(1000, 15, 31)
+    assert sklearn_uses_brute(50, 10, 31) and not sklearn_uses_brute(63, 10, 30)
+
+
+def test_shard_bounds():
+    from palantir_b200._dist import shard_bounds
+
+    b = shard_bounds(1_000_000, 8, 256)
+    assert b[0] == 0 and b[-1] == 1_000_000 and all(x % 256 == 0 for x in b[1:-1])
+    assert all(b[i] <= b[i + 1] for i in range(8))
+    assert shard_bounds(100, 4, 256) == [0, 0, 0, 0, 100]
+    assert shard_bounds(1185, 8) == [0, 148, 296, 444, 592, 740, 888, 1036, 1185]
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from palantir_b200 import _dist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+n, k = 1000, 5
+q0, nq = _dist.row_shard(n, 256)
+full_i = torch.arange(n * k, dtype=torch.int32).reshape(n, k)
+full_d = torch.arange(n * k, dtype=torch.float64).reshape(n, k) * 0.5
+gi, gd = _dist.allgather_rows(full_i[q0:q0 + nq].clone(), full_d[q0:q0 + nq].clone(), n, 256)
+assert torch.equal(gi, full_i) and torch.equal(gd, full_d), "allgather mismatch"
+v = torch.full((7,), float(dist.get_rank() + 1), dtype=torch.float64)
+_dist.allreduce_sum_(v)
+assert torch.all(v == 3.0)
+b = torch.full((3,), float(dist.get_rank()), dtype=torch.float64)
+_dist.broadcast_(b, 0)
+assert torch.all(b == 0.0)
+# waypoint (source) shards cover all rows exactly once
+bounds = _dist.shard_bounds(1185, 2)
+assert bounds == [0, 592, 1185]
+dist.destroy_process_group()
+print("ok", dist.get_rank() if False else sys.argv[3])
+'''
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = str(s.getsockname()[1])
+    s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=180)
+        assert p.returncode == 0, err
+        assert "ok" in out
