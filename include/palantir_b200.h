@@ -28,6 +28,8 @@ const char* pb200_last_error(void);
 int pb200_abi_version(void);
 int pb200_set_device(int dev);
 int pb200_device_sync(void);
+/* kernel launches issued by the library since load (bench.py's gpu_launches) */
+long long pb200_launch_count(void);
 
 /* ---- exact kNN in PCA space: sklearn NearestNeighbors(brute).kneighbors, utils.py:404-407 ---- */
 
@@ -41,10 +43,12 @@ int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, 
 
 /* FP32 candidate generation: for query points q0..q0+nq-1 of xtq (q0 % 256 == 0) keep the k_keep (<= 48)
  * smallest scores |y|^2 - 2 x.y over all n_ref_pad references.  out_idx/out_score [nq][k_keep] ascending,
- * out_thr[nq] = k_keep-th score (lower bound for every excluded reference; +inf if nothing excluded). */
+ * out_thr[nq] = k_keep-th score (lower bound for every excluded reference; +inf if nothing excluded).
+ * scratch: lists[ceil(nq/256)*256*64] 64-bit words (per-row candidate buffers). */
 int pb200_knn_candidates_f32(const float* xtq, long long nq_pad, const float* xtr, long long n_ref_pad,
-                             const float* yn, int q0, int nq, int d, int d_pad, int k_keep, int* out_idx,
-                             float* out_score, float* out_thr, void* stream);
+                             const float* yn, int q0, int nq, int d, int d_pad, int k_keep,
+                             unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
+                             void* stream);
 
 /* FP64 re-rank with the reference's expanded-form distance; out_idx/out_dist [nq][k] ascending by
  * (distance, index); flag[nq] = 1 where the FP32 error bound cannot certify the row; n_flagged[1]. */

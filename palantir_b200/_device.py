@@ -144,9 +144,11 @@ def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
     cand = empty((nq, k_keep), I32)
     score = empty((nq, k_keep), F32)
     thr = empty((nq,), F32)
+    lists = empty((round_up(nq, 256) * 64,), I64)
     with stage("knn_candidates"):
         call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.xt, prep.ld, prep.yn, q0, nq, prep.d,
-             prep.d_pad, k_keep, cand, score, thr)
+             prep.d_pad, k_keep, lists, cand, score, thr)
+    del lists
     flag = empty((nq,), U8)
     n_flagged = empty((1,), I32)
     with stage("knn_rerank"):

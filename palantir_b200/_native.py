@@ -81,7 +81,7 @@ def load():
             fn = getattr(lib, name, None)
             if fn is None:
                 raise NativeLibraryError(f"{LIB_PATH} does not export {name} (stale build?)")
-            fn.restype = ctypes.c_char_p if name == "pb200_last_error" else ctypes.c_int
+            fn.restype = {"p": ctypes.c_char_p, "l": ctypes.c_longlong}.get(ret, ctypes.c_int)
             fn.argtypes = [_CODES[c] for c in codes]
         _lib = lib
     return _lib
@@ -127,3 +127,8 @@ def call(name: str, *args):
     rc = fn(*[_arg(a) for a in args], stream_ptr())
     if rc != 0:
         raise NativeLibraryError(f"{name} failed ({rc}): {lib.pb200_last_error().decode()}")
+
+
+def launch_count() -> int:
+    """Kernel launches issued by the library so far (0 if it was never loaded)."""
+    return int(_lib.pb200_launch_count()) if _lib is not None else 0

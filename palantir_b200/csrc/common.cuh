@@ -11,8 +11,11 @@ namespace pb200 {
 void set_error(const char* where, cudaError_t e);
 void set_error_msg(const char* msg);
 
+void count_launch();
+
 #define PB_CHECK_LAUNCH(name)                                  \
   do {                                                         \
+    pb200::count_launch();                                     \
     cudaError_t _e = cudaGetLastError();                       \
     if (_e != cudaSuccess) { pb200::set_error(name, _e); return (int)_e; } \
   } while (0)
@@ -57,6 +60,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(a), "r"(parity)
         : "memory");
   } while (!ok);
+}
+// non-blocking phase test
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 // global -> shared bulk copy (bytes % 16 == 0, both addresses 16-B aligned),
 // completion counted on an mbarrier in the same CTA.

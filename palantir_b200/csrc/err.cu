@@ -12,8 +12,12 @@ void set_error_msg(const char* msg) {
   strncpy(g_err, msg, sizeof(g_err) - 1);
   g_err[sizeof(g_err) - 1] = 0;
 }
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 }  // namespace pb200
 
+// Number of kernel launches issued by this library since it was loaded.
+extern "C" long long pb200_launch_count(void) { return (long long)pb200::g_launches; }
 extern "C" const char* pb200_last_error(void) { return pb200::g_err; }
 extern "C" int pb200_abi_version(void) { return 1; }
 // Bind the calling thread to a device (the library links its own static CUDA

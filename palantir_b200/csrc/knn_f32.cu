@@ -17,12 +17,13 @@
 // memory and moves with ONE bulk copy; the last chunk of a tile carries only
 // k_tail = round_up(d - 16 (KCH-1), 4) coordinate rows.  The point count is padded
 // to a multiple of 256.  A CTA owns 256 query rows and streams every 128-point
-// reference tile through a 3-stage shared-memory ring filled by the TMA engine
+// reference tile through an 8-stage shared-memory ring filled by the TMA engine
 // (cp.async.bulk + mbarrier full/empty pairs; whichever warp reaches a chunk first
-// issues the copies for the chunk two ahead, so no warp waits on a fixed producer).  16 consumer warps each own 16
+// issues the copies for the chunk seven ahead, so no warp waits on a fixed producer).  16 consumer warps each own 16
 // query rows x 128 reference columns (8x8 register micro-tile per thread), so the
-// top-K lists of a row are only ever touched by one warp and the selection needs
-// no CTA-wide barrier.  One CTA per SM (512 threads, <=128 registers; a 17th,
+// top-K lists of a row (L2-resident global scratch; only the per-row count and
+// threshold live in shared memory, which leaves room for an 8-deep ring) are only
+// ever touched by one warp and the selection needs no CTA-wide barrier.  One CTA per SM (512 threads, <=128 registers; a 17th,
 // dedicated producer warp would cap registers at 96).
 #include "common.cuh"
 
@@ -30,24 +31,23 @@ namespace pb200 {
 
 constexpr int KNN_BM = 256;       // query rows per CTA
 constexpr int KNN_BN = 128;       // reference points per tile
-constexpr int KNN_DK = 16;        // coordinates per pipeline stage
-constexpr int KNN_NST = 3;        // pipeline stages
+constexpr int KNN_DK = 16;        // coordinates per pipeline chunk
+constexpr int KNN_NST = 8;        // pipeline stages (chunks in flight)
 constexpr int KNN_CAP = 64;       // per-row candidate buffer capacity
 constexpr int KNN_HIGH = 56;      // compaction trigger
 constexpr int KNN_MAX_KEEP = 48;  // max K_keep
-constexpr int KNN_CONSUMER_WARPS = 16;
-constexpr int KNN_THREADS = KNN_CONSUMER_WARPS * 32;
+constexpr int KNN_WARPS = 16;
+constexpr int KNN_THREADS = KNN_WARPS * 32;
+constexpr int KNN_BLOCK_FLOATS = KNN_DK * KNN_BN;  // one (tile, kc) operand block = 8 KB
 
 struct KnnStage {
   float a[2][KNN_DK][KNN_BN];  // two 128-row query tiles
   float b[KNN_DK][KNN_BN];
   float yn[KNN_BN];
 };
-constexpr int KNN_BLOCK_FLOATS = KNN_DK * KNN_BN;  // one (tile, kc) operand block
 
 struct KnnSmem {
   KnnStage st[KNN_NST];
-  unsigned long long buf[KNN_BM][KNN_CAP];
   int cnt[KNN_BM];
   float thr[KNN_BM];
   uint64_t full[KNN_NST];
@@ -65,6 +65,7 @@ struct KnnParams {
   int kch;           // d_pad / 16
   int k_tail;        // coordinate rows in the last chunk of a tile (multiple of 4, <= 16)
   int k_keep;
+  unsigned long long* lists;  // [tiles*256][64] packed (score, index) candidate buffers (L2-resident scratch)
   int* out_idx;      // [nq][k_keep]
   float* out_score;  // [nq][k_keep]
   float* out_thr;    // [nq]
@@ -74,29 +75,50 @@ __device__ __forceinline__ unsigned long long pack_entry(float s, int idx) {
   return ((unsigned long long)f32_ordered(s) << 32) | (unsigned int)idx;
 }
 
-// Warp-collective: keep the k_keep smallest entries of a row's buffer (rank by
-// counting; keys are unique because the index is part of the key).
-__device__ __forceinline__ void compact_row(KnnSmem& sm, int row, int k_keep, int lane) {
+// Issue the bulk copies of pipeline chunk g into its (already released) stage; one thread.
+__device__ __noinline__ void knn_produce(KnnSmem* smp, const KnnParams* pp, int g, int qtile0) {
+  KnnSmem& sm = *smp;
+  const KnnParams& p = *pp;
+  const int KCH = p.kch;
+  const int t = g / KCH, kc = g - t * KCH;
+  const int st = g % KNN_NST;
+  const bool last = (kc == KCH - 1);
+  const uint32_t blk_bytes = (uint32_t)(last ? p.k_tail : KNN_DK) * KNN_BN * 4u;
+  mbar_arrive_expect_tx(&sm.full[st], 3u * blk_bytes + (last ? KNN_BN * 4u : 0u));
+  const float* a0 = p.xtq + ((long long)qtile0 * KCH + kc) * KNN_BLOCK_FLOATS;
+  const float* a1 = a0 + (long long)KCH * KNN_BLOCK_FLOATS;
+  const float* br = p.xtr + ((long long)t * KCH + kc) * KNN_BLOCK_FLOATS;
+  bulk_g2s(&sm.st[st].a[0][0][0], a0, blk_bytes, &sm.full[st]);
+  bulk_g2s(&sm.st[st].a[1][0][0], a1, blk_bytes, &sm.full[st]);
+  bulk_g2s(&sm.st[st].b[0][0], br, blk_bytes, &sm.full[st]);
+  if (last) bulk_g2s(&sm.st[st].yn[0], p.yn + (long long)t * KNN_BN, KNN_BN * 4, &sm.full[st]);
+}
+
+// Warp-collective: rank the (<= 64) buffered entries of a row (keys are unique because
+// the index is part of the key), keep the k_keep smallest, tighten the row threshold.
+__device__ __noinline__ void knn_compact_row(KnnSmem* smp, unsigned long long* buf, int row, int k_keep, int lane) {
+  KnnSmem& sm = *smp;
   int c = sm.cnt[row];
   c = c < KNN_CAP ? c : KNN_CAP;
-  unsigned long long e0 = lane < c ? sm.buf[row][lane] : ~0ull;
-  unsigned long long e1 = lane + 32 < c ? sm.buf[row][lane + 32] : ~0ull;
+  const unsigned long long e0 = lane < c ? __ldcg(buf + lane) : ~0ull;
+  const unsigned long long e1 = lane + 32 < c ? __ldcg(buf + lane + 32) : ~0ull;
   int r0 = 0, r1 = 0;
 #pragma unroll 8
   for (int j = 0; j < 32; ++j) {
-    unsigned long long o0 = __shfl_sync(0xffffffffu, e0, j);
-    unsigned long long o1 = __shfl_sync(0xffffffffu, e1, j);
+    const unsigned long long o0 = __shfl_sync(0xffffffffu, e0, j);
+    const unsigned long long o1 = __shfl_sync(0xffffffffu, e1, j);
     r0 += (o0 < e0) + (o1 < e0);
     r1 += (o0 < e1) + (o1 < e1);
   }
   __syncwarp();
-  if (lane < c && r0 < k_keep) sm.buf[row][r0] = e0;
-  if (lane + 32 < c && r1 < k_keep) sm.buf[row][r1] = e1;
+  if (lane < c && r0 < k_keep) __stcg(buf + r0, e0);
+  if (lane + 32 < c && r1 < k_keep) __stcg(buf + r1, e1);
   if (c >= k_keep) {
     if (lane < c && r0 == k_keep - 1) sm.thr[row] = f32_from_ordered((uint32_t)(e0 >> 32));
     if (lane + 32 < c && r1 == k_keep - 1) sm.thr[row] = f32_from_ordered((uint32_t)(e1 >> 32));
   }
   if (lane == 0) sm.cnt[row] = c < k_keep ? c : k_keep;
+  __threadfence_block();
   __syncwarp();
 }
 
@@ -106,8 +128,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int qbase = p.q0 + blockIdx.x * KNN_BM;  // column in xtq
+  const int qbase = p.q0 + blockIdx.x * KNN_BM;  // first query point of this CTA
   const int row_local0 = blockIdx.x * KNN_BM;    // row in the output arrays
+  unsigned long long* lists = p.lists + (long long)row_local0 * KNN_CAP;
 
   for (int r = tid; r < KNN_BM; r += KNN_THREADS) {
     sm.cnt[r] = 0;
@@ -116,7 +139,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
   if (tid == 0) {
     for (int s = 0; s < KNN_NST; ++s) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], KNN_CONSUMER_WARPS);
+      mbar_init(&sm.empty[s], KNN_WARPS);
     }
     fence_mbar_init();
   }
@@ -124,36 +147,20 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
 
   const int T = p.n_ref_tiles;
   const int KCH = p.kch;
-
-  // ---------------- producer: issued by whichever warp gets there first ---------------
-  // Chunk g = t*KCH + kc lives in stage g % NST.  Before refilling a stage the issuing
-  // thread waits on its "empty" barrier (all 16 warps done with the previous tenant).
   const int total_chunks = T * KCH;
   const int qtile0 = qbase / KNN_BN;
-  auto produce = [&](int g) {
-    const int t = g / KCH, kc = g - t * KCH;
-    const int st = g % KNN_NST;
-    const uint32_t ph = (uint32_t)(g / KNN_NST) & 1u;
-    mbar_wait(&sm.empty[st], ph ^ 1u);
-    const bool last = (kc == KCH - 1);
-    const uint32_t blk_bytes = (uint32_t)(last ? p.k_tail : KNN_DK) * KNN_BN * 4u;
-    mbar_arrive_expect_tx(&sm.full[st], 3u * blk_bytes + (last ? KNN_BN * 4u : 0u));
-    const float* a0 = p.xtq + ((long long)qtile0 * KCH + kc) * KNN_BLOCK_FLOATS;
-    const float* a1 = a0 + (long long)KCH * KNN_BLOCK_FLOATS;
-    const float* br = p.xtr + ((long long)t * KCH + kc) * KNN_BLOCK_FLOATS;
-    bulk_g2s(&sm.st[st].a[0][0][0], a0, blk_bytes, &sm.full[st]);
-    bulk_g2s(&sm.st[st].a[1][0][0], a1, blk_bytes, &sm.full[st]);
-    bulk_g2s(&sm.st[st].b[0][0], br, blk_bytes, &sm.full[st]);
-    if (last) bulk_g2s(&sm.st[st].yn[0], p.yn + (long long)t * KNN_BN, KNN_BN * 4, &sm.full[st]);
-  };
+  // Chunk g = t*KCH + kc lives in stage g % NST.  There is no producer warp and nobody
+  // ever blocks on an "empty" barrier: at the top of every chunk each warp's lane 0 tests
+  // (non-blocking) whether the stage of the next un-issued chunk has been released by all 16
+  // warps and, if so, claims it (CAS) and issues its bulk copies -- in practice the warp that
+  // released the stage last refills it a few cycles later.
   if (tid == 0) {
     int g = 0;
-    for (; g < KNN_NST - 1 && g < total_chunks; ++g) produce(g);
+    for (; g < KNN_NST && g < total_chunks; ++g) knn_produce(&sm, &p, g, qtile0);
     sm.next_chunk = g;
   }
   __syncthreads();
 
-  // ---------------- consumers ---------------------------------------------------------
   const int r0 = warp * 16 + (lane >> 4) * 8;  // first of this thread's 8 rows (CTA-local)
   const int a_off = (r0 >> 7) * KNN_BLOCK_FLOATS + (r0 & 127);
   const int c0 = (lane & 15) * 4;              // columns c0..c0+3 and 64+c0..64+c0+3
@@ -170,32 +177,22 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
 
     for (int kc = 0; kc < KCH; ++kc, ++gchunk) {
       if (lane == 0) {
-        const int target = gchunk + KNN_NST - 1;
-        if (target < total_chunks && *(volatile int*)&sm.next_chunk == target &&
+        const int target = *(volatile int*)&sm.next_chunk;
+        if (target < total_chunks &&
+            mbar_test(&sm.empty[target % KNN_NST], (((uint32_t)(target / KNN_NST)) & 1u) ^ 1u) &&
             atomicCAS(&sm.next_chunk, target, target + 1) == target)
-          produce(target);
+          knn_produce(&sm, &p, target, qtile0);
       }
+      __syncwarp();
       mbar_wait(&sm.full[stage], phase);
       const float* As = &sm.st[stage].a[0][0][0] + a_off;
       const float* Bs = &sm.st[stage].b[0][0] + c0;
-      if (kc < KCH - 1 || p.k_tail == KNN_DK) {
+      const int klen = (kc == KCH - 1) ? p.k_tail : KNN_DK;
+#pragma unroll 1
+      for (int k0 = 0; k0 < klen; k0 += 4) {
 #pragma unroll
-        for (int k = 0; k < KNN_DK; ++k) {
-          const float4 a0 = *reinterpret_cast<const float4*>(As + k * KNN_BN);
-          const float4 a1 = *reinterpret_cast<const float4*>(As + k * KNN_BN + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN);
-          const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN + 64);
-          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-      } else {
-        const int kt = p.k_tail;
-#pragma unroll 4
-        for (int k = 0; k < kt; ++k) {
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = k0 + kk;
           const float4 a0 = *reinterpret_cast<const float4*>(As + k * KNN_BN);
           const float4 a1 = *reinterpret_cast<const float4*>(As + k * KNN_BN + 4);
           const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN);
@@ -244,7 +241,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
               const int pos = atomicAdd(&sm.cnt[row], 1);
               if (pos < KNN_CAP) {
                 const int col = colbase + (j < 4 ? c0 + j : 64 + c0 + (j - 4));
-                sm.buf[row][pos] = pack_entry(s, col);
+                __stcg(lists + row * KNN_CAP + pos, pack_entry(s, col));
                 acc[i][j] = -INFINITY;  // s becomes +inf: never pushed twice
               } else {
                 fail = true;
@@ -252,10 +249,11 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
             }
           }
         }
+        __threadfence_block();
         __syncwarp();
         for (int rr = 0; rr < 16; ++rr) {
           const int row = warp * 16 + rr;
-          if (sm.cnt[row] >= KNN_HIGH) compact_row(sm, row, p.k_keep, lane);
+          if (sm.cnt[row] >= KNN_HIGH) knn_compact_row(&sm, lists + row * KNN_CAP, row, p.k_keep, lane);
         }
         if (!__any_sync(0xffffffffu, fail)) break;
       }
@@ -269,8 +267,9 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
     if (grow >= p.nq) continue;  // warp-uniform
     int c = sm.cnt[row];
     c = c < KNN_CAP ? c : KNN_CAP;
-    const unsigned long long e0 = lane < c ? sm.buf[row][lane] : ~0ull;
-    const unsigned long long e1 = lane + 32 < c ? sm.buf[row][lane + 32] : ~0ull;
+    const unsigned long long* buf = lists + row * KNN_CAP;
+    const unsigned long long e0 = lane < c ? __ldcg(buf + lane) : ~0ull;
+    const unsigned long long e1 = lane + 32 < c ? __ldcg(buf + lane + 32) : ~0ull;
     int q0r = 0, q1r = 0;
 #pragma unroll 8
     for (int j = 0; j < 32; ++j) {
@@ -441,8 +440,9 @@ int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, 
 }
 
 int pb200_knn_candidates_f32(const float* xtq, long long nq_pad, const float* xtr, long long n_ref_pad,
-                             const float* yn, int q0, int nq, int d, int d_pad, int k_keep, int* out_idx,
-                             float* out_score, float* out_thr, void* stream) {
+                             const float* yn, int q0, int nq, int d, int d_pad, int k_keep,
+                             unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
+                             void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (k_keep < 1 || k_keep > KNN_MAX_KEEP || q0 % KNN_BM != 0 || n_ref_pad % KNN_BM != 0 ||
       nq_pad % KNN_BM != 0 || d_pad % KNN_DK != 0 || d_pad < KNN_DK || d < 1 || d > d_pad ||
@@ -460,7 +460,7 @@ int pb200_knn_candidates_f32(const float* xtq, long long nq_pad, const float* xt
   p.xtq = xtq; p.xtr = xtr; p.yn = yn;
   p.q0 = q0; p.nq = nq; p.n_ref_tiles = (int)(n_ref_pad / KNN_BN); p.kch = d_pad / KNN_DK; p.k_keep = k_keep;
   p.k_tail = ((d - (d_pad - KNN_DK)) + 3) / 4 * 4;
-  p.out_idx = out_idx; p.out_score = out_score; p.out_thr = out_thr;
+  p.lists = lists; p.out_idx = out_idx; p.out_score = out_score; p.out_thr = out_thr;
   static bool attr_set = false;
   const int smem = (int)sizeof(KnnSmem);
   if (!attr_set) {

@@ -1,0 +1,373 @@
+"""GPU parity tests: the CUDA path (reached through the C-ABI library) against the CPU
+oracle on the same seeded inputs, against the reference outputs committed under
+tests/golden/, and -- at benchmark sizes -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): kNN indices exact (sets per row; ties excepted),
+kernel values <= 1e-12 relative, eigenvalues <= 1e-5 relative, eigenvector subspace angle
+< 1e-4 (vs the converged oracle), pseudotime max-abs <= 1e-4 and Spearman > 0.999, fate
+probabilities max-abs <= 1e-4.
+"""
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+from scipy.linalg import subspace_angles
+from scipy.sparse import csr_matrix
+from scipy.stats import spearmanr
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import palantir_b200
+    from palantir_b200 import _native
+
+    _native.load()
+    return palantir_b200
+
+
+@pytest.fixture(scope="module")
+def po():
+    from oracle import palantir_oracle
+
+    return palantir_oracle
+
+
+def _knn(pb, x, k):
+    from palantir_b200 import _device as dv
+
+    idx, dist, stats = dv.knn_like_sklearn(dv.to_device(np.ascontiguousarray(x)), k)
+    return idx.cpu().numpy(), dist.cpu().numpy(), stats
+
+
+def _rows_equal_as_sets(a, b):
+    return sum(set(r) == set(s) for r, s in zip(a, b))
+
+
+# ------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("name,rtol", [("dm_f32_n1500_d20.npz", 0.0), ("dm_f64_n800_d24.npz", 1e-12),
+                                       ("dm_f64_n600_d8.npz", 0.0)])
+def test_knn_matches_reference_fixture(pb, name, rtol):
+    z = golden(name)
+    idx, dist, stats = _knn(pb, z["x"], int(z["knn"]) + 1)
+    assert _rows_equal_as_sets(idx, z["knn_ind"]) == idx.shape[0]
+    got, ref = np.sort(dist, 1)[:, 1:], np.sort(z["knn_dist"], 1)[:, 1:]      # column 0 = self (rounding noise)
+    if rtol == 0.0:
+        assert np.array_equal(got, ref)          # f32 input: sqrtf-quantised, bit-equal; kd-tree case: exact
+    else:
+        assert np.max(np.abs(got - ref) / ref) <= rtol
+
+
+@pytest.mark.parametrize("n,d,k,dtype", [
+    (50, 10, 31, np.float64),      # reference-test size: k+1 >= N//2 -> brute, N < one tile
+    (257, 16, 31, np.float32),     # ragged: one row past a 256 tile, d = one chunk
+    (1000, 50, 31, np.float32),    # d with a partial last chunk (48 + 4 -> tail)
+    (3000, 100, 31, np.float32),   # config-3 dimensionality
+    (777, 130, 11, np.float64),    # d > 128, small k
+    (2000, 3, 30, np.float64),     # kd-tree rule (d <= 15): direct differences
+    (600, 20, 50, np.float32),     # k wider than the candidate buffers -> exact path
+])
+def test_knn_matches_sklearn_live(pb, po, n, d, k, dtype):
+    rng = np.random.default_rng(n + d)
+    x = (rng.normal(size=(n, d)) * rng.uniform(0.2, 3.0, size=d)).astype(dtype)
+    ref_d, ref_i = po.knn_with_self(x, k)
+    idx, dist, stats = _knn(pb, x, k)
+    bad = [r for r in range(n) if set(idx[r]) != set(ref_i[r])]
+    # a mismatch is only admissible at an exact / rounding-level tie of the k-th distance
+    for r in bad:
+        assert abs(np.sort(dist[r])[-1] - np.sort(ref_d[r])[-1]) <= 1e-12 * max(1.0, ref_d[r].max())
+    assert len(bad) <= max(1, n // 500)
+    tol = 0.0 if dtype == np.float32 and d > 15 else 1e-11
+    a, b = np.sort(dist, 1)[:, 1:], np.sort(ref_d, 1)[:, 1:]
+    assert np.max(np.abs(a - b)) <= tol * max(1.0, b.max()) + (0 if tol else 0)
+
+
+def test_knn_with_duplicate_points(pb, po):
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(400, 24)).astype(np.float32)
+    x[100:110] = x[0:10]                      # exact duplicates: zero distances, ties
+    ref_d, ref_i = po.knn_with_self(x, 16)
+    idx, dist, _ = _knn(pb, x, 16)
+    assert np.array_equal(np.sort(dist, 1)[:, 2:], np.sort(ref_d, 1)[:, 2:])
+    # every returned neighbour is a true k-NN (distance not larger than the reference's k-th)
+    assert np.all(np.sort(dist, 1)[:, -1] <= np.sort(ref_d, 1)[:, -1])
+
+
+# ------------------------------------------------------------------ kernel, T, eigensolver
+@pytest.mark.parametrize("name", ["dm_f32_n1500_d20.npz", "dm_f64_n600_d8.npz", "dm_f64_n800_d24.npz"])
+def test_diffusion_maps_match_reference_fixture(pb, name):
+    z = golden(name)
+    res = pb.utils.run_diffusion_maps(pd.DataFrame(z["x"]), n_components=10, knn=int(z["knn"]),
+                                      kernel_backend="sklearn")
+    k = res["kernel"]
+    assert isinstance(k, csr_matrix) and set(res) == {"T", "EigenVectors", "EigenValues", "kernel"}
+    assert np.array_equal(k.indptr, z["k_indptr"]) and np.array_equal(k.indices, z["k_indices"])
+    assert np.max(np.abs(k.data - z["k_data"]) / z["k_data"]) <= 1e-12
+    assert np.max(np.abs(res["T"].data - z["t_data"]) / z["t_data"]) <= 1e-12
+    ev = res["EigenValues"].values
+    assert np.max(np.abs(ev - z["evals_tight"]) / np.abs(z["evals_tight"])) <= 1e-5
+    assert np.max(np.abs(ev - z["evals_asis"])) <= 1e-4          # the reference's own test tolerance
+    v = res["EigenVectors"].values
+    assert subspace_angles(v, z["evecs_tight"]).max() < 1e-4
+    assert np.allclose(np.linalg.norm(v, axis=0), 1.0, atol=1e-12)
+    assert np.min(np.abs(np.sum(v * z["evecs_tight"], axis=0))) > 1 - 1e-8      # equal up to sign, per vector
+
+
+def test_kernel_alpha_and_tiny_input(pb, po):
+    z = golden("tiny_50x10.npz")
+    k = pb.utils.compute_kernel(pd.DataFrame(z["x"]), backend="sklearn")
+    assert np.array_equal(k.indices, z["k_indices"])
+    assert np.max(np.abs(k.data - z["k_data"]) / z["k_data"]) <= 1e-12
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(700, 20))
+    ka = pb.utils.compute_kernel(pd.DataFrame(x), knn=10, alpha=0.5, backend="sklearn")
+    ko = po.adaptive_kernel(x, 10, 0.5)
+    ko.sort_indices()
+    assert np.array_equal(ka.indices, ko.indices)
+    assert np.max(np.abs(ka.data - ko.data) / ko.data) <= 1e-12
+
+
+def test_diffusion_maps_from_kernel_reference_tests(pb):
+    """tests/test_utils_diffusion_maps_from_kernel.py of the reference, same assertions."""
+    from scipy.sparse.linalg import eigs
+
+    rng = np.random.default_rng(0)
+    a = rng.random((50, 50))
+    kern = csr_matrix((a + a.T) / 2)
+    r = pb.utils.diffusion_maps_from_kernel(kern)
+    assert r["T"].shape == (50, 50) and r["EigenVectors"].shape == (50, 10) and r["EigenValues"].shape == (10,)
+    assert pb.utils.diffusion_maps_from_kernel(kern, n_components=5)["EigenVectors"].shape == (50, 5)
+    r2 = pb.utils.diffusion_maps_from_kernel(kern, seed=0)
+    assert np.allclose(r["EigenValues"], r2["EigenValues"])
+    e, _ = eigs(r["T"].toarray(), 10, tol=1e-4, maxiter=1000)
+    assert np.allclose(r["EigenValues"], np.real(sorted(e, reverse=True)[:10]), atol=1e-4)
+    assert pb.utils.determine_multiscale_space(r).shape[0] == 50
+
+
+def test_run_diffusion_maps_anndata_keys(pb):
+    from palantir_b200.compat import AnnDataLike
+
+    z = golden("dm_f64_n600_d8.npz")
+    ad = AnnDataLike(np.zeros((600, 2)))
+    ad.obsm["X_pca"] = z["x"]
+    res = pb.utils.run_diffusion_maps(ad, n_components=10, kernel_backend="sklearn")
+    assert ad.obsp["DM_Kernel"] is res["kernel"] and ad.obsp["DM_Similarity"] is res["T"]
+    assert np.array_equal(ad.obsm["DM_EigenVectors"], res["EigenVectors"].values)
+    assert np.array_equal(ad.uns["DM_EigenValues"], res["EigenValues"].values)
+    k2 = pb.utils.compute_kernel(ad, knn=10, alpha=0.5, kernel_key="custom")
+    assert "custom" in ad.obsp and isinstance(k2, csr_matrix)
+    with pytest.warns(UserWarning):
+        pb.utils.run_diffusion_maps(res["kernel"])            # sparse input = kernel
+
+
+# ------------------------------------------------------------------ run_palantir
+def test_max_min_sampling_known_answer(pb):
+    z = golden("ref_known_answers.npz")
+    wp = pb.core._max_min_sampling(pd.DataFrame(z["mm_data"]), num_waypoints=9, seed=0)
+    assert list(wp) == list(z["mm_waypoints"])
+
+
+def test_compute_pseudotime_known_answer(pb):
+    """tests/test_core_equivalence.py:117-132 of the reference (atol = rtol = 1e-10)."""
+    z = golden("ref_known_answers.npz")
+    b = pd.DataFrame(z["pt_data"], index=[f"cell_{i}" for i in range(25)])
+    pt, w = pb.core._compute_pseudotime(b, "cell_0", knn=5, waypoints=b.index[z["pt_waypoints"]], n_jobs=1,
+                                        max_iterations=10)
+    assert np.allclose(pt.values, z["pt_pseudotime"], atol=1e-10, rtol=1e-10)
+    assert np.allclose(w.values, z["pt_w"], atol=1e-10, rtol=1e-10)
+
+
+def test_run_palantir_matches_reference_fixture(pb, names1500):
+    z = golden("palantir_n1500_wp200.npz")
+    names = names1500
+    ms = pd.DataFrame(z["ms"], index=names)
+    pr = pb.core.run_palantir(ms, names[int(z["early"])], terminal_states=list(names[z["terminals"]]),
+                              num_waypoints=int(z["num_waypoints"]), knn=int(z["knn"]))
+    assert isinstance(pr, pb.PResults)
+    assert list(names.get_indexer(pr.waypoints)) == list(z["waypoints"])          # identical waypoints
+    assert np.max(np.abs(pr.pseudotime.values - z["pseudotime"])) <= 1e-4
+    assert spearmanr(pr.pseudotime.values, z["pseudotime"])[0] > 0.999
+    assert list(names.get_indexer(pr.branch_probs.columns)) == list(z["fate_columns"])
+    assert np.max(np.abs(pr.branch_probs.values - z["fate_probs"])) <= 1e-4
+    assert np.max(np.abs(pr.entropy.values - z["entropy"])) <= 1e-4
+    # much tighter in practice (FP64 shortest paths / refinement / solve)
+    assert np.max(np.abs(pr.pseudotime.values - z["pseudotime"])) <= 1e-10
+
+
+def test_run_palantir_vs_oracle_other_settings(pb, po, names1500):
+    z = golden("palantir_n1500_wp200.npz")
+    names, ms = names1500, z["ms"]
+    for kw in (dict(scale_components=False), dict(use_early_cell_as_start=True), dict(knn=12, num_waypoints=60)):
+        o = po.run_palantir(ms, int(z["early"]), terminal=list(z["terminals"]), **{"num_waypoints": 120, **kw})
+        pr = pb.core.run_palantir(pd.DataFrame(ms, index=names), names[int(z["early"])],
+                                  terminal_states=list(names[z["terminals"]]), **{"num_waypoints": 120, **kw})
+        assert list(names.get_indexer(pr.waypoints)) == list(o["waypoints"]), kw
+        assert np.max(np.abs(pr.pseudotime.values - o["pseudotime"])) <= 1e-9, kw
+        assert np.max(np.abs(pr.branch_probs.values - o["fate_probs"])) <= 1e-9, kw
+
+
+def test_run_palantir_reference_api_behaviour(pb):
+    """tests/test_core_run_palantir.py of the reference (sizes and assertions)."""
+    from palantir_b200.compat import AnnDataLike
+
+    rng = np.random.default_rng(11)
+    df = pd.DataFrame(rng.random((50, 10)), columns=[f"c{i}" for i in range(10)],
+                      index=[f"cell_{i}" for i in range(50)])
+    pr = pb.core.run_palantir(df, "cell_0")                                   # terminal states auto-detected
+    assert isinstance(pr, pb.PResults) and len(pr.pseudotime) == 50
+    ad = AnnDataLike(np.zeros((50, 3)), obs_names=df.index)
+    ad.obsm["DM_EigenVectors_multiscaled"] = df.values
+    pb.core.run_palantir(ad, "cell_0")
+    for key in ("palantir_pseudotime", "palantir_entropy"):
+        assert key in ad.obs
+    assert "palantir_fate_probabilities" in ad.obsm and "palantir_waypoints" in ad.uns
+    pr2 = pb.core.run_palantir(df, "cell_0", terminal_states=["cell_1", "cell_2"])
+    assert "cell_1" in pr2.branch_probs.columns and "cell_2" in pr2.branch_probs.columns
+    a = pb.core.run_palantir(df, "cell_0", terminal_states=["cell_1", "cell_2"], scale_components=True)
+    b = pb.core.run_palantir(df, "cell_0", terminal_states=["cell_1", "cell_2"], scale_components=False)
+    assert not np.array_equal(a.pseudotime.values, b.pseudotime.values)
+    with pytest.raises(ValueError):
+        pb.core.run_palantir(df, "cell_0", knn=0)
+    ts = pd.Series({"cell_1": "A", "cell_2": "B"})
+    pb.core.run_palantir(ad, "cell_0", terminal_states=ts, save_as_df=False)
+    assert list(ad.uns["palantir_fate_probabilities_columns"]) == ["A", "B"]
+
+
+# ------------------------------------------------------------------ stage kernels
+def _random_knn_graph(n, m, k, seed):
+    from sklearn.neighbors import NearestNeighbors
+
+    rng = np.random.default_rng(seed)
+    data = rng.random((n, m))
+    adj = NearestNeighbors(n_neighbors=k).fit(data).kneighbors_graph(data, mode="distance")
+    return data, adj
+
+
+def test_sssp_bit_exact_vs_scipy_dijkstra(pb):
+    from scipy.sparse import csgraph
+
+    from palantir_b200 import _device as dv, _device_core as dc
+
+    data, adj = _random_knn_graph(4000, 3, 8, 0)
+    idx, dist, _ = dc.knn_table(dv.to_device(data), 8)
+    g = dc.undirected_graph(idx, dist)
+    src = np.array([0, 17, 3999, 1234, 2048], dtype=np.int64)
+    for delta in (None, 1e-3, 1e9):
+        D, stats = dc.sssp(g, dv.to_device(src), delta=delta, want_stats=True)
+        ref = csgraph.dijkstra(adj, directed=False, indices=src)
+        assert np.array_equal(D.cpu().numpy(), ref)                  # +inf where unreachable, bit-equal elsewhere
+
+
+def test_connect_graph_reconnects_like_the_reference(pb, po):
+    rng = np.random.default_rng(4)
+    a = rng.normal(size=(300, 4))
+    b = rng.normal(size=(40, 4)) + 25.0                  # a far-away island: unreachable with knn = 5
+    x = np.vstack([a, b])
+    names = pd.Index([f"c{i:04d}" for i in range(x.shape[0])])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = po.run_palantir(x, 0, terminal=[50, 320], num_waypoints=40, knn=5, scale_components=False)
+        with pytest.warns(UserWarning):
+            pr = pb.core.run_palantir(pd.DataFrame(x, index=names), names[0], terminal_states=[names[50], names[320]],
+                                      num_waypoints=40, knn=5, scale_components=False)
+    assert list(names.get_indexer(pr.waypoints)) == list(o["waypoints"])
+    assert np.all(np.isfinite(pr.pseudotime.values))
+    assert np.max(np.abs(pr.pseudotime.values - o["pseudotime"])) <= 1e-9
+    assert np.max(np.abs(pr.branch_probs.values - o["fate_probs"])) <= 1e-9
+
+
+def test_markov_chain_and_absorption_vs_oracle(pb, po):
+    from palantir_b200 import _device as dv, _device_core as dc
+
+    rng = np.random.default_rng(8)
+    wp = rng.random((500, 5))
+    pt = rng.random(500)
+    T = dc.markov_chain_dense(dv.to_device(wp), 30, dv.to_device(pt)).cpu().numpy()
+    To = po.markov_chain(wp, 30, pt).toarray()
+    assert np.max(np.abs(T - To)) <= 1e-13
+    abs_states = np.array([3, 77, 401])
+    B = dc.absorption_probabilities(dv.to_device(To), abs_states).cpu().numpy()
+    rows, _, Bo = po.absorption_probabilities(csr_matrix(To), abs_states)
+    full = np.empty_like(Bo)
+    full[rows] = Bo
+    assert np.max(np.abs(B - full)) <= 1e-11
+
+
+def test_dense_solve_vs_numpy(pb):
+    from palantir_b200 import _device as dv
+
+    rng = np.random.default_rng(1)
+    for n, r in ((1, 1), (7, 3), (300, 5), (1201, 3)):
+        a = rng.normal(size=(n, n)) + n * np.eye(n) * 0.05
+        b = rng.normal(size=(n, r))
+        ad, bd = dv.to_device(a), dv.to_device(b)
+        sing = dv.empty((1,), dv.I32)
+        dv.call("pb200_dense_solve_f64", ad, bd, n, r, sing)
+        x = np.linalg.solve(a, b)
+        assert int(sing.item()) == 0
+        assert np.max(np.abs(bd.cpu().numpy() - x)) <= 1e-9 * max(1.0, np.abs(x).max())
+
+
+def test_spmv_vs_scipy(pb):
+    from palantir_b200 import _device as dv
+
+    z = golden("dm_f32_n1500_d20.npz")
+    k = csr_matrix((z["k_data"], z["k_indices"], z["k_indptr"]), shape=(1500, 1500))
+    kd = dv.csr_from_host(k)
+    x = np.random.default_rng(0).normal(size=1500)
+    y = dv.empty((1500,), dv.F64)
+    dv.call("pb200_csr_spmv_f64", kd.indptr, kd.indices, kd.data, 1500, kd.nnz, dv.to_device(x), y)
+    assert np.max(np.abs(y.cpu().numpy() - k @ x)) <= 1e-12
+
+
+def test_magic_imputation_vs_oracle(pb, po):
+    z = golden("dm_f64_n600_d8.npz")
+    res = pb.utils.run_diffusion_maps(pd.DataFrame(z["x"]), kernel_backend="sklearn")
+    rng = np.random.default_rng(0)
+    x = rng.random((600, 37)).astype(np.float32)
+    got = pb.utils.run_magic_imputation(x, dm_res=res, n_steps=3, sparse=False)
+    ref = po.magic_impute(res["T"], x, 3)
+    near_clip = np.abs(ref - 1e-2) < 1e-5
+    assert np.max(np.abs(got - ref)[~near_clip]) <= 1e-5
+    sp = pb.utils.run_magic_imputation(pd.DataFrame(x), dm_res=res)
+    assert isinstance(sp, pd.DataFrame) and sp.shape == x.shape
+    assert isinstance(pb.utils.run_magic_imputation(x, dm_res=res), csr_matrix)
+
+
+# ------------------------------------------------------------------ benchmark-size properties
+def test_properties_at_benchmark_scale(pb):
+    """Config 2 (100k cells x 50 PCs, 1200 waypoints): properties that hold at any size."""
+    from palantir_b200.datasets import synth_branching, synth_names
+
+    n = 100_000
+    x, info = synth_branching(n, 50, seed=0)
+    names = synth_names(n)
+    res = pb.utils.run_diffusion_maps(pd.DataFrame(x, index=names), kernel_backend="sklearn")
+    k, t = res["kernel"], res["T"]
+    assert abs(k - k.T).max() == 0.0                                       # K = W + W^T is exactly symmetric
+    assert np.all(np.diff(k.indptr) >= 30) and k.has_sorted_indices
+    assert np.max(np.abs(np.asarray(t.sum(axis=1)).ravel() - 1.0)) < 1e-12   # T row-stochastic
+    lam = res["EigenValues"].values
+    assert abs(lam[0] - 1.0) < 1e-10 and np.all(np.diff(lam) <= 0)
+    v = res["EigenVectors"].values
+    resid = np.linalg.norm(t @ v - v * lam, axis=0)
+    assert resid.max() < 1e-8                                              # converged eigenpairs of T
+    ms = pb.utils.determine_multiscale_space(res)
+    term = {names[p]: b for b, p in info["terminals"].items()}
+    pr = pb.core.run_palantir(ms, names[info["early"]], terminal_states=term, num_waypoints=1200)
+    pt = pr.pseudotime.values
+    assert pt.min() == 0.0 and pt.max() == 1.0
+    assert spearmanr(pt, info["time"])[0] > 0.98
+    bp = pr.branch_probs.values
+    assert bp.shape == (n, 3) and np.all(bp >= 0) and np.all(bp.sum(1) <= 1 + 1e-9) and np.all(bp.sum(1) > 0.97)
+    for cell in term:
+        assert pr.branch_probs.loc[cell].max() > 0.9
+    assert pr.entropy.values.min() >= 0
