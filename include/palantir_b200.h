@@ -72,6 +72,18 @@ int pb200_fma_peak_f32(float* scratch, int blocks, int iters, void* stream);
 int pb200_knn_direct_f64(const double* data, long long n, int m, const double* query, const int* qrows, int q0,
                          int nq, int k, int* out_idx, double* out_dist, void* stream);
 
+/* Same search on cells sorted ascending by column 0 with exact first-coordinate pruning; indices are
+ * positions in the sorted order; tiles_scanned (optional) counts visited 128-point tiles. */
+int pb200_knn_sorted_f64(const double* data, long long n, int m, int q0, int nq, int k, int* out_idx,
+                         double* out_dist, unsigned long long* tiles_scanned, void* stream);
+/* locality ordering: perm[i] = index of the i-th smallest data[:, col]; inv[perm[i]] = i */
+long long pb200_argsort_scratch_bytes(long long n);
+int pb200_argsort_col_f64(const double* data, long long n, int m, int col, int* perm, int* inv, void* scratch,
+                          long long scratch_bytes, void* stream);
+/* out[i] = a[perm[i]]  /  out[perm[i]] = a[i]   (rows of m doubles) */
+int pb200_permute_rows_f64(const double* a, long long n, int m, const int* perm, double* out, void* stream);
+int pb200_unpermute_rows_f64(const double* a, long long n, int m, const int* perm, double* out, void* stream);
+
 /* ---- adaptive kernel / CSR construction: utils.py:408-417, 440-446, 478-480 ---- */
 int pb200_knn_self_first(const int* idx, long long n, int kc, int* flag_out, void* stream);
 int pb200_adaptive_weights(const double* dist, long long n, int kc, int col0, int ka, double* w, void* stream);

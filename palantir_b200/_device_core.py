@@ -82,6 +82,45 @@ def knn_table(data: torch.Tensor, knn: int):
     return idx, dist, stats
 
 
+def locality_order(dev: torch.Tensor):
+    """Sort the cells along the first column.  Returns (perm, inv, sorted copy):
+    sorted[i] = dev[perm[i]], inv[perm[i]] = i."""
+    n, m = dev.shape
+    lib = _native.load()
+    nbytes = int(lib.pb200_argsort_scratch_bytes(n))
+    scratch = empty((nbytes,), torch.uint8)
+    perm, inv = empty((n,), I32), empty((n,), I32)
+    call("pb200_argsort_col_f64", dev, n, m, 0, perm, inv, scratch, nbytes)
+    out = empty((n, m), F64)
+    call("pb200_permute_rows_f64", dev, n, m, perm, out)
+    return perm, inv, out
+
+
+def knn_table_sorted(dsort: torch.Tensor, knn: int):
+    """Self-including neighbour table of cells already sorted along column 0 (exact, pruned);
+    indices are sorted positions; rows sharded across ranks."""
+    n, m = dsort.shape
+    if knn > n:
+        raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {knn}, n_samples_fit = {n}")
+    q0, nq = _dist.row_shard(n, 256)
+    idx = empty((nq, knn), I32)
+    dist = empty((nq, knn), F64)
+    scanned = zeros((1,), I64)
+    with stage("knn_direct"):
+        call("pb200_knn_sorted_f64", dsort, n, m, q0, nq, knn, idx, dist, scanned)
+    idx, dist = _dist.allgather_rows(idx, dist, n, 256)
+    return idx, dist, {"method": "direct-sorted", "flagged": 0, "scanned": scanned}
+
+
+def unpermute_rows(a: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """out[perm[i]] = a[i] (rows)."""
+    n = a.shape[0]
+    m = 1 if a.dim() == 1 else a.shape[1]
+    out = torch.empty_like(a)
+    call("pb200_unpermute_rows_f64", a.contiguous(), n, m, perm, out)
+    return out
+
+
 def undirected_graph(idx: torch.Tensor, dist: torch.Tensor) -> dv.DeviceCSR:
     """Symmetric CSR with min(w_ij, w_ji) on the union pattern, self loops dropped: the graph
     csgraph.dijkstra(directed=False) effectively walks (core.py:362)."""

@@ -64,19 +64,38 @@ def _boundary_positions(dev: torch.Tensor) -> np.ndarray:
 
 def _compute_pseudotime_device(dev: torch.Tensor, start_pos: int, knn: int, wp_pos: np.ndarray,
                                max_iterations: int):
-    """core.py:353-401 on positions.  Returns (pseudotime tensor [N], D shard, row0, colsum, sdv)."""
+    """core.py:353-401 on positions.  When sklearn would pick its kd-tree (<= 15 columns) the
+    stage runs on cells sorted along the first component (pruned exact kNN, L2-friendly
+    shortest paths).  Returns (pseudotime [N] in input order, D shard [rows, N] and colsum [N] in
+    WORK order, row0, sdv, perm) with perm = None when work order == input order, else
+    work[i] = input[perm[i]]."""
     print("Shortest path distances using {}-nearest neighbor graph...".format(knn))
     t0 = time.time()
-    idx, dist, kstats = dc.knn_table(dev, knn)
-    g = dc.connect_graph(idx, dist, dev, start_pos)
-    n_wp = len(wp_pos)
+    n, m = dev.shape
+    if knn > n:
+        raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {knn}, n_samples_fit = {n}")
+    wp_pos = np.asarray(wp_pos, dtype=np.int64)
+    if not dv.sklearn_uses_brute(n, m, knn):
+        perm, inv, work = dc.locality_order(dev)
+        idx, dist, kstats = dc.knn_table_sorted(work, knn)
+        inv_h = inv.cpu().numpy().astype(np.int64)
+        start_w, wp_w = int(inv_h[start_pos]), inv_h[wp_pos]
+    else:
+        perm, work = None, dev
+        idx, dist, kstats = dc.knn_table(dev, knn)
+        start_w, wp_w = int(start_pos), wp_pos
+    g = dc.connect_graph(idx, dist, work, start_w)
+    n_wp = len(wp_w)
     rank, size = _dist.world()
     bounds = _dist.shard_bounds(n_wp, size)
     row0, row1 = bounds[rank], bounds[rank + 1]
-    sources = dv.to_device(np.ascontiguousarray(wp_pos[row0:row1], dtype=np.int64))
+    sources = dv.to_device(np.ascontiguousarray(wp_w[row0:row1], dtype=np.int64))
     D, stats = dc.sssp(g, sources, want_stats=dv.PROFILE is not None)
     if dv.PROFILE is not None:
         torch.cuda.synchronize()
+        if "scanned" in kstats:
+            kstats = dict(kstats, scanned=int(kstats["scanned"].item()))
+    kstats = {k: v for k, v in kstats.items() if not isinstance(v, torch.Tensor)}
     LAST_INFO["sssp"] = {
         "sources": int(row1 - row0), "arcs": int(g.nnz), "knn": kstats,
         "rounds_mean": float(stats[:, 0].double().mean().item()) if stats is not None and stats.numel() else None,
@@ -85,10 +104,11 @@ def _compute_pseudotime_device(dev: torch.Tensor, start_pos: int, knn: int, wp_p
     }
     print("Time for shortest paths: {} minutes".format((time.time() - t0) / 60))
     print("Iteratively refining the pseudotime...")
-    start_row = int(np.flatnonzero(wp_pos == start_pos)[0])
-    wp_cells = dv.to_device(np.ascontiguousarray(wp_pos, dtype=np.int64))
-    pt, colsum, sdv = dc.refine_pseudotime(D, row0, n_wp, wp_cells, start_row, max_iterations)
-    return pt, D, row0, colsum, sdv
+    start_row = int(np.flatnonzero(wp_w == start_w)[0])
+    wp_cells = dv.to_device(np.ascontiguousarray(wp_w, dtype=np.int64))
+    pt_w, colsum, sdv = dc.refine_pseudotime(D, row0, n_wp, wp_cells, start_row, max_iterations)
+    pt = pt_w if perm is None else dc.unpermute_rows(pt_w, perm)
+    return pt, D, row0, colsum, sdv, perm
 
 
 def _compute_pseudotime(data: pd.DataFrame, start_cell, knn: int, waypoints: pd.Index, n_jobs: int,
@@ -101,11 +121,15 @@ def _compute_pseudotime(data: pd.DataFrame, start_cell, knn: int, waypoints: pd.
     dev = dv.to_device(np.ascontiguousarray(data.values, dtype=np.float64))
     start_pos = int(np.where(data.index == start_cell)[0][0])
     wp_pos = data.index.get_indexer(waypoints)
-    pt, D, row0, colsum, sdv = _compute_pseudotime_device(dev, start_pos, int(knn), wp_pos, max_iterations)
+    pt, D, row0, colsum, sdv, perm = _compute_pseudotime_device(dev, start_pos, int(knn), wp_pos, max_iterations)
     if _dist.world()[1] > 1:
         raise NotImplementedError("_compute_pseudotime returns the dense W and is single-GPU only")
     Dh = D.cpu().numpy()
     W = np.exp(-0.5 * np.power(Dh / sdv, 2)) / colsum.cpu().numpy()[None, :]
+    if perm is not None:                      # columns back to the input order
+        Wo = np.empty_like(W)
+        Wo[:, perm.cpu().numpy()] = W
+        W = Wo
     return (pd.Series(pt.cpu().numpy(), index=data.index),
             pd.DataFrame(W, index=waypoints, columns=data.index))
 
@@ -234,7 +258,7 @@ def run_palantir(data, early_cell, terminal_states=None, knn: int = 30, num_wayp
     print("Determining pseudotime...")
     start_pos = int(index.get_loc(start_cell))
     wp_pos = index.get_indexer(waypoints)
-    pt_dev, D, row0, colsum, sdv = _compute_pseudotime_device(dev, start_pos, knn, wp_pos, max_iterations)
+    pt_dev, D, row0, colsum, sdv, perm = _compute_pseudotime_device(dev, start_pos, knn, wp_pos, max_iterations)
 
     print("Entropy and branch probabilities...")
     wp_pos_d = dv.to_device(np.ascontiguousarray(wp_pos, dtype=np.int64))
@@ -245,6 +269,8 @@ def run_palantir(data, early_cell, terminal_states=None, knn: int = 30, num_wayp
     print("Project results to all cells...")
     B_local = B[row0:row0 + D.shape[0]].contiguous()
     fates_dev, ent_dev = dc.project_fates(D, sdv, colsum, B_local)
+    if perm is not None:
+        fates_dev, ent_dev = dc.unpermute_rows(fates_dev, perm), dc.unpermute_rows(ent_dev, perm)
 
     pseudotime = pd.Series(pt_dev.cpu().numpy(), index=index)
     branch_probs = pd.DataFrame(fates_dev.cpu().numpy(), index=index, columns=term_labels)
@@ -312,8 +338,7 @@ def identify_terminal_states(ms_data: pd.DataFrame, early_cell, knn: int = 30, n
     waypoints = pd.Index(waypoints.difference([start_cell]).unique())
     waypoints = pd.Index([start_cell]).append(waypoints)
     wp_pos = index.get_indexer(waypoints)
-    pt_dev, _, _, _, _ = _compute_pseudotime_device(dev, int(index.get_loc(start_cell)), int(knn), wp_pos,
-                                                    max_iterations)
+    pt_dev = _compute_pseudotime_device(dev, int(index.get_loc(start_cell)), int(knn), wp_pos, max_iterations)[0]
     wp_pos_d = dv.to_device(np.ascontiguousarray(wp_pos, dtype=np.int64))
     wp_dev = dc.gather_rows(dev, wp_pos_d)
     pt_wp_dev = dc.gather_rows(pt_dev, wp_pos_d)

@@ -83,6 +83,125 @@ __global__ void __launch_bounds__(KD_ROWS) knn_direct_kernel(const double* __res
   }
 }
 
+// Same search on cells SORTED by their first coordinate, with exact pruning: the CTA
+// walks the 128-point reference tiles outwards from its own position and stops on a side
+// once the squared first-coordinate gap to that tile is >= the largest current k-th
+// distance of its 128 rows.  The bound is safe in floating point: rounding is monotone, so
+// fl((x0_q - x0_p)^2) >= fl(gap^2) for every point p beyond the tile edge, and adding the
+// other (non-negative) terms cannot decrease the rounded sum.  Indices are positions in the
+// sorted order.
+template <int M>
+__global__ void __launch_bounds__(KD_ROWS) knn_sorted_kernel(const double* __restrict__ data, long long n, int q0,
+                                                             int nq, int k, int* __restrict__ out_idx,
+                                                             double* __restrict__ out_dist,
+                                                             unsigned long long* __restrict__ tiles_scanned) {
+  __shared__ double tile[KD_TILE][M];
+  __shared__ double s_red[KD_ROWS / 32];
+  __shared__ double s_maxworst;
+  const int tid = threadIdx.x;
+  const long long qb0 = (long long)q0 + (long long)blockIdx.x * KD_ROWS;
+  const long long q = qb0 + tid;
+  const bool active = (long long)blockIdx.x * KD_ROWS + tid < nq;
+  double x[M];
+  {
+    const long long src = active ? q : qb0;
+#pragma unroll
+    for (int c = 0; c < M; ++c) x[c] = data[src * M + c];
+  }
+  long long q_last = qb0 + KD_ROWS - 1;
+  if (q_last > (long long)q0 + nq - 1) q_last = (long long)q0 + nq - 1;
+  const double xq_lo = data[qb0 * M], xq_hi = data[q_last * M];
+  double bd[KD_KMAX];
+  int bi[KD_KMAX];
+  for (int s = 0; s < k; ++s) { bd[s] = INFINITY; bi[s] = -1; }
+  double worst = INFINITY;
+  if (tid == 0) s_maxworst = INFINITY;
+  __syncthreads();
+  const long long ntiles = (n + KD_TILE - 1) / KD_TILE;
+  long long right = qb0 / KD_TILE, left = right - 1;
+  bool r_done = false, l_done = false;
+  unsigned long long scanned = 0;
+  int turn = 0;
+  while (!(r_done && l_done)) {
+    const bool go_right = (turn == 0 && !r_done) || l_done;
+    turn ^= 1;
+    long long t;
+    if (go_right) {
+      if (right >= ntiles) { r_done = true; continue; }
+      double gap = data[right * KD_TILE * M] - xq_hi;
+      gap = gap > 0.0 ? gap : 0.0;
+      if (__dmul_rn(gap, gap) >= s_maxworst) { r_done = true; continue; }
+      t = right++;
+    } else {
+      if (left < 0) { l_done = true; continue; }
+      long long lastp = left * KD_TILE + KD_TILE - 1;
+      if (lastp > n - 1) lastp = n - 1;
+      double gap = xq_lo - data[lastp * M];
+      gap = gap > 0.0 ? gap : 0.0;
+      if (__dmul_rn(gap, gap) >= s_maxworst) { l_done = true; continue; }
+      t = left--;
+    }
+    const long long t0 = t * KD_TILE;
+    __syncthreads();
+    for (int e = tid; e < KD_TILE * M; e += KD_ROWS) {
+      const long long g = t0 * M + e;
+      (&tile[0][0])[e] = g < n * M ? data[g] : 0.0;
+    }
+    __syncthreads();
+    ++scanned;
+    const int lim = (int)((n - t0) < KD_TILE ? (n - t0) : KD_TILE);
+    if (active) {
+#pragma unroll 4
+      for (int j = 0; j < lim; ++j) {
+        double r = 0.0;
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          const double df = __dsub_rn(x[c], tile[j][c]);
+          r = __dadd_rn(r, __dmul_rn(df, df));
+        }
+        if (r < worst) {
+          int pos = k - 1;
+          while (pos > 0 && bd[pos - 1] > r) {
+            bd[pos] = bd[pos - 1];
+            bi[pos] = bi[pos - 1];
+            --pos;
+          }
+          bd[pos] = r;
+          bi[pos] = (int)(t0 + j);
+          worst = bd[k - 1];
+        }
+      }
+    }
+    double w = active ? worst : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = w;
+    __syncthreads();
+    if (tid == 0) {
+      double mw = s_red[0];
+      for (int qq = 1; qq < KD_ROWS / 32; ++qq) mw = fmax(mw, s_red[qq]);
+      s_maxworst = mw;
+    }
+    __syncthreads();
+  }
+  if (active) {
+    const long long row = (long long)blockIdx.x * KD_ROWS + tid;
+    for (int s = 0; s < k; ++s) {
+      out_idx[row * k + s] = bi[s];
+      out_dist[row * k + s] = sqrt(bd[s]);
+    }
+  }
+  if (tid == 0 && tiles_scanned) atomicAdd(tiles_scanned, scanned);
+}
+
+template <int M>
+static int launch_sorted(const double* data, long long n, int q0, int nq, int k, int* out_idx, double* out_dist,
+                         unsigned long long* tiles_scanned, cudaStream_t st) {
+  knn_sorted_kernel<M><<<div_up(nq, KD_ROWS), KD_ROWS, 0, st>>>(data, n, q0, nq, k, out_idx, out_dist, tiles_scanned);
+  PB_CHECK_LAUNCH("knn_sorted_kernel");
+  return 0;
+}
+
 template <int M>
 static int launch_direct(const double* data, long long n, const double* query, const int* qrows, int q0, int nq,
                          int k, int* out_idx, double* out_dist, cudaStream_t st) {
@@ -110,6 +229,26 @@ int pb200_knn_direct_f64(const double* data, long long n, int m, const double* q
   if (nq <= 0) return 0;
   switch (m) {
 #define PB_CASE(M) case M: return launch_direct<M>(data, n, query, qrows, q0, nq, k, out_idx, out_dist, st);
+    PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
+    PB_CASE(9) PB_CASE(10) PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15) PB_CASE(16)
+#undef PB_CASE
+  }
+  return -1;
+}
+
+// Same result on data sorted ascending by column 0 (rows q0..q0+nq-1 are the queries, q0 % 128 == 0);
+// indices refer to the sorted order.  tiles_scanned (optional, device) accumulates the number of
+// 128-point tiles visited.
+int pb200_knn_sorted_f64(const double* data, long long n, int m, int q0, int nq, int k, int* out_idx,
+                         double* out_dist, unsigned long long* tiles_scanned, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m < 1 || m > 16 || k < 1 || k > KD_KMAX || k > n || q0 % KD_TILE != 0) {
+    set_error_msg("pb200_knn_sorted_f64: need 1 <= m <= 16, 1 <= k <= min(64, n), q0 % 128 == 0");
+    return -1;
+  }
+  if (nq <= 0) return 0;
+  switch (m) {
+#define PB_CASE(M) case M: return launch_sorted<M>(data, n, q0, nq, k, out_idx, out_dist, tiles_scanned, st);
     PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
     PB_CASE(9) PB_CASE(10) PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15) PB_CASE(16)
 #undef PB_CASE

@@ -1,0 +1,99 @@
+// Locality ordering of the cells for the pseudotime stage.
+//
+// The multiscale diffusion space is close to a one-dimensional curve.
+// Sorting the cells along its first component makes (a) the exact low-dimensional kNN
+// prunable (a reference tile whose first-coordinate gap already exceeds the current
+// k-th distance cannot contribute) and (b) the shortest-path frontier touch a narrow,
+// L2-resident index window.  The sort itself is CUB's device radix sort on the
+// order-preserving bit pattern of the FP64 key (plumbing; the kernels that use the
+// order are hand-written).
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+namespace pb200 {
+
+__global__ void sort_keys_kernel(const double* __restrict__ data, long long n, int m, int col,
+                                 unsigned long long* __restrict__ keys, int* __restrict__ iota) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long u = (unsigned long long)__double_as_longlong(data[i * m + col]);
+  u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+  keys[i] = u;
+  iota[i] = (int)i;
+}
+
+__global__ void invert_perm_kernel(const int* __restrict__ perm, long long n, int* __restrict__ inv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = (int)i;
+}
+
+// out[i][:] = a[perm[i]][:]
+__global__ void permute_rows_kernel(const double* __restrict__ a, long long n, int m, const int* __restrict__ perm,
+                                    double* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * m) return;
+  const long long i = e / m;
+  out[e] = a[(long long)perm[i] * m + (e - i * m)];
+}
+
+// out[perm[i]][:] = a[i][:]
+__global__ void unpermute_rows_kernel(const double* __restrict__ a, long long n, int m, const int* __restrict__ perm,
+                                      double* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * m) return;
+  const long long i = e / m;
+  out[(long long)perm[i] * m + (e - i * m)] = a[e];
+}
+
+}  // namespace pb200
+
+using namespace pb200;
+
+extern "C" {
+
+// Bytes of scratch pb200_argsort_col_f64 needs for n keys.
+long long pb200_argsort_scratch_bytes(long long n) {
+  size_t temp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const int*)nullptr, (int*)nullptr, (int)n);
+  const size_t al = 256;
+  size_t tot = (temp + al - 1) / al * al;
+  tot += ((size_t)n * 8 + al - 1) / al * al * 2;   // keys in / out
+  tot += ((size_t)n * 4 + al - 1) / al * al;       // iota
+  return (long long)tot;
+}
+
+// perm[i] = index of the i-th smallest data[:, col] (stable); inv[perm[i]] = i.
+int pb200_argsort_col_f64(const double* data, long long n, int m, int col, int* perm, int* inv, void* scratch,
+                          long long scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n >= 2147483647LL) { set_error_msg("pb200_argsort_col_f64: n too large"); return -1; }
+  if (scratch_bytes < pb200_argsort_scratch_bytes(n)) { set_error_msg("pb200_argsort_col_f64: scratch too small"); return -1; }
+  const size_t al = 256;
+  char* p = (char*)scratch;
+  unsigned long long* kin = (unsigned long long*)p;  p += ((size_t)n * 8 + al - 1) / al * al;
+  unsigned long long* kout = (unsigned long long*)p; p += ((size_t)n * 8 + al - 1) / al * al;
+  int* iota = (int*)p;                               p += ((size_t)n * 4 + al - 1) / al * al;
+  size_t temp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp, kin, kout, iota, perm, (int)n);
+  sort_keys_kernel<<<div_up(n, 256), 256, 0, st>>>(data, n, m, col, kin, iota);
+  PB_CHECK_LAUNCH("sort_keys_kernel");
+  PB_CHECK(cub::DeviceRadixSort::SortPairs((void*)p, temp, kin, kout, iota, perm, (int)n, 0, 64, st));
+  invert_perm_kernel<<<div_up(n, 256), 256, 0, st>>>(perm, n, inv);
+  PB_CHECK_LAUNCH("invert_perm_kernel");
+  return 0;
+}
+
+int pb200_permute_rows_f64(const double* a, long long n, int m, const int* perm, double* out, void* stream) {
+  permute_rows_kernel<<<div_up(n * m, 256), 256, 0, (cudaStream_t)stream>>>(a, n, m, perm, out);
+  PB_CHECK_LAUNCH("permute_rows_kernel");
+  return 0;
+}
+
+int pb200_unpermute_rows_f64(const double* a, long long n, int m, const int* perm, double* out, void* stream) {
+  unpermute_rows_kernel<<<div_up(n * m, 256), 256, 0, (cudaStream_t)stream>>>(a, n, m, perm, out);
+  PB_CHECK_LAUNCH("unpermute_rows_kernel");
+  return 0;
+}
+
+}  // extern "C"

@@ -60,13 +60,15 @@ def run_device(x_dev: torch.Tensor, early_pos: int, terminal_pos: Optional[Seque
         if terminal_pos is not None:
             wp = np.union1d(wp, np.asarray(list(terminal_pos), dtype=np.int64))
         wp = np.concatenate([[start_pos], wp[wp != start_pos]]).astype(np.int64)
-        pt, D, row0, colsum, sdv = core._compute_pseudotime_device(dev, start_pos, knn, wp, max_iterations)
+        pt, D, row0, colsum, sdv, perm = core._compute_pseudotime_device(dev, start_pos, knn, wp, max_iterations)
         wp_d = dv.to_device(wp)
         wp_dev = dc.gather_rows(dev, wp_d)
         pt_wp = dc.gather_rows(pt, wp_d)
         term_labels, B = core._differentiation_entropy_device(
             wp_dev, pd.Index(wp), None if terminal_pos is None else list(terminal_pos), knn, pt_wp)
         fates, ent = dc.project_fates(D, sdv, colsum, B[row0:row0 + D.shape[0]].contiguous())
+        if perm is not None:
+            fates, ent = dc.unpermute_rows(fates, perm), dc.unpermute_rows(ent, perm)
     return dict(kernel=kern, t_values=tvals, eigenvalues=lam, eigenvectors=U, multiscale=ms, pseudotime=pt,
                 fate_probs=fates, entropy=ent, waypoints=wp, terminal=np.asarray(term_labels), knn=kstats,
                 nnz=kern.nnz, D_rows=int(D.shape[0]))
