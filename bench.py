@@ -262,7 +262,9 @@ def run_gpu_arm(args):
     fp32_peak = 148 * 8 * 1024 * 16384 * 16 * 2 / p0.elapsed_time(p1) / 1e9          # TFLOP/s
     nq_rank = -(-n // world)
     knn_ms = prof.get("knn_candidates", float("nan"))
-    knn_tf = 2.0 * nq_rank * n * d / knn_ms / 1e9 if knn_ms == knn_ms else None
+    knn_alg_tf = 2.0 * nq_rank * n * d / knn_ms / 1e9 if knn_ms == knn_ms else None
+    visited = (out["knn"] or {}).get("tiles_visited_frac") or 1.0
+    knn_tf = knn_alg_tf * visited if knn_alg_tf else None          # FLOPs actually executed
     # SpMV timed alone on the symmetric operator of the last step
     kd = out["kernel"]
     xs = torch.rand(n, dtype=torch.float64, device="cuda")
@@ -305,7 +307,9 @@ def run_gpu_arm(args):
                      "achieved": knn_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": (knn_tf / fp32_peak) if knn_tf else None, "traffic": None,
                      "peak_source": "FFMA probe pb200_fma_peak_f32 timed in this run (MEASURED_PEAKS.json has no FP32 "
-                                    "figure)", "algorithmic": "2*Nq*Nr*d FLOP per launch", "ms_per_launch": knn_ms},
+                                    "figure)", "algorithmic": "2*Nq*Nr*d FLOP per launch x fraction of 256x128 tiles visited (exact "
+                                    "projection pruning skips the rest); 'effective' counts the skipped tiles too",
+                     "tiles_visited_frac": visited, "effective_tflops": knn_alg_tf, "ms_per_launch": knn_ms},
         "roofline_spmv": {"bound": "hbm", "kernel": "csr_spmv_kernel<16>", "achieved": spmv_gbs, "peak": hbm_peak,
                           "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                           "algorithmic": "12*nnz + 4*(N+1) + 16*N bytes per launch", "ms_per_launch": spmv_ms},

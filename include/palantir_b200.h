@@ -33,37 +33,58 @@ long long pb200_launch_count(void);
 
 /* ---- exact kNN in PCA space: sklearn NearestNeighbors(brute).kneighbors, utils.py:404-407 ---- */
 
-/* Column means, centred FP32 copy xt[d_pad * ld] in the tiled k-major layout the candidate kernel
- * streams (point i = 128*tile + il, coordinate c = 16*kc + k at ((tile*(d_pad/16) + kc)*16 + k)*128 + il),
- * FP32 score norms yn[ld] (+inf on padding), FP64 centred norms xcn[n], FP64 row norms of the original
- * data xn64[n], max centred norm^2 rmax2[1].
- * d <= 1024, d_pad % 16 == 0, d_pad - d < 16, ld % 256 == 0.  col_sums: d doubles of scratch. */
-int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, long long ld, double* col_sums,
-                      float* xt, float* yn, double* xcn, double* xn64, double* rmax2, void* stream);
+/* mean[d] = column means of x[n][d] (float32 or float64 input). */
+int pb200_col_means(const void* x, int is_f64, long long n, int d, double* mean, void* stream);
+/* proj[r] = (float)(x[r] - mean) . v   (FP64 accumulate; the FP32-rounded centred points are what the
+ * candidate kernel works on).  With out[c] = sum_r w[r] (x[r][c] - mean[c]) this is one step of the power
+ * iteration that finds the leading principal axis used as sort / pruning direction. */
+int pb200_project_rows(const void* x, int is_f64, long long n, int d, const double* mean, const double* v,
+                       double* proj, void* stream);
+int pb200_weighted_col_sums(const void* x, int is_f64, long long n, int d, const double* mean, const double* w,
+                            double* out, void* stream);
 
-/* FP32 candidate generation: for query points q0..q0+nq-1 of xtq (q0 % 256 == 0) keep the k_keep (<= 48)
- * smallest scores |y|^2 - 2 x.y over all n_ref_pad references.  out_idx/out_score [nq][k_keep] ascending,
- * out_thr[nq] = k_keep-th score (lower bound for every excluded reference; +inf if nothing excluded).
- * scratch: lists[ceil(nq/256)*256*64] 64-bit words (per-row candidate buffers). */
-int pb200_knn_candidates_f32(const float* xtq, long long nq_pad, const float* xtr, long long n_ref_pad,
-                             const float* yn, int q0, int nq, int d, int d_pad, int k_keep,
-                             unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
-                             void* stream);
-
-/* FP64 re-rank with the reference's expanded-form distance; out_idx/out_dist [nq][k] ascending by
- * (distance, index); flag[nq] = 1 where the FP32 error bound cannot certify the row; n_flagged[1]. */
-int pb200_knn_rerank_f64(const void* x, int is_f64, const double* xn64, const double* xcn, const double* rmax2,
-                         long long n, int d, int q0, int nq, const int* cand, const float* thr32, int k_keep,
-                         int k, int* out_idx, double* out_dist, unsigned char* flag, int* n_flagged,
+/* Centred FP32 copy xt[d_pad * ld] of the points in WORK order (work point i = input row perm[i]; perm may be
+ * NULL) in the tiled k-major layout the candidate kernel streams (point i = 128*tile + il, coordinate
+ * c = 16*kc + k at ((tile*(d_pad/16) + kc)*16 + k)*128 + il), FP32 score norms yn[ld] (+inf on padding),
+ * FP64 centred norms xcn[n], FP64 row norms of the original data xn64[n] (all in work order), max centred
+ * norm^2 rmax2[1].  d <= 1024, d_pad % 16 == 0, d_pad - d < 16, ld % 256 == 0. */
+int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, long long ld, const double* mean,
+                      const int* perm, float* xt, float* yn, double* xcn, double* xn64, double* rmax2,
+                      void* stream);
+/* lo[t] / hi[t] = projection of the first / last point of work-order tile t (proj indexed by input row). */
+int pb200_tile_intervals(const double* proj, const int* perm, long long n, long long ntiles, double* lo, double* hi,
                          void* stream);
+
+/* FP32 candidate generation: for work-order points q0..q0+nq-1 (q0 % 256 == 0) keep the k_keep (<= 48)
+ * smallest scores |y|^2 - 2 x.y over all n_pad points.  With tile_lo / tile_hi (projection intervals of the
+ * 128-point tiles of points sorted along a unit direction; NULL = none) reference tiles that provably cannot
+ * contribute are skipped.  out_idx/out_score [nq][k_keep] ascending (work-order indices), out_thr[nq] =
+ * k_keep-th score (lower bound for every excluded reference; +inf if nothing excluded).
+ * scratch: lists[ceil(nq/256)*256*64] 64-bit words; tiles_visited: optional counter. */
+int pb200_knn_candidates_f32(const float* xt, long long n_pad, const float* yn, const double* xcn,
+                             const double* tile_lo, const double* tile_hi, int q0, int nq, int d, int d_pad,
+                             int k_keep, unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
+                             unsigned long long* tiles_visited, void* stream);
+
+/* FP64 re-rank with the reference's expanded-form distance; candidates are work-order indices, x is the
+ * input matrix (row of work point j = perm[j]; perm may be NULL); out_idx [nq][k] holds INPUT-order indices,
+ * rows are in work order, ascending by (distance, input index); flag[nq] = 1 where the FP32 error bound
+ * cannot certify the row; n_flagged[1]. */
+int pb200_knn_rerank_f64(const void* x, int is_f64, const int* perm, const double* xn64, const double* xcn,
+                         const double* rmax2, long long n, int d, int q0, int nq, const int* cand,
+                         const float* thr32, int k_keep, int k, int* out_idx, double* out_dist,
+                         unsigned char* flag, int* n_flagged, void* stream);
 
 /* rows_out[0..counter) = indices (relative to q0) of flagged rows. */
 int pb200_knn_flagged_rows(const unsigned char* flag, int nq, int* rows_out, int* counter, void* stream);
 
 /* Exact FP64 brute force for the listed rows.  scratch: n_ctas * n doubles. */
-int pb200_knn_exact_rows_f64(const void* x, int is_f64, const double* xn64, long long n, int d, const int* rows,
-                             int n_rows, int q0, int k, double* scratch, int n_ctas, int* out_idx,
-                             double* out_dist, void* stream);
+int pb200_knn_exact_rows_f64(const void* x, int is_f64, const int* perm, const double* xn64, long long n, int d,
+                             const int* rows, int n_rows, int q0, int k, double* scratch, int n_ctas,
+                             int* out_idx, double* out_dist, void* stream);
+/* out[perm[i]][:] = in[i][:]: neighbour-table rows from work order back to input order */
+int pb200_knn_unpermute(const int* idx, const double* dist, long long n, int k, const int* perm, int* out_idx,
+                        double* out_dist, void* stream);
 
 /* Roofline probe: blocks x 1024 threads x iters x 16 FFMAs. */
 int pb200_fma_peak_f32(float* scratch, int blocks, int iters, void* stream);
@@ -145,10 +166,9 @@ int pb200_point_dists_expanded(const double* data, long long n, int m, long long
 
 /* ---- multi-source shortest paths: scipy.sparse.csgraph.dijkstra(directed=False), core.py:362 ---- */
 int pb200_sssp_num_ctas(int n_sources);
-/* D[n_sources][n]; scratch: q[n_ctas*3*n] int, bits[n_ctas*2*ceil(n/32)] uint32; stats [n_sources][3] or NULL */
+/* D[n_sources][n]; scratch: q[n_ctas*3*n] int, marks[n_ctas*2*n] int; stats [n_sources][3] or NULL */
 int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
-                     int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,
-                     void* stream);
+                     int n_sources, double delta, double* D, int* q, int* marks, long long* stats, void* stream);
 
 /* ---- pseudotime refinement and projection (core.py:368-397, 225-230) ---- */
 int pb200_sum_pow_f64(const double* x, long long count, double shift, int power, double* partial, double* out,

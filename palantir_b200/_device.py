@@ -92,38 +92,79 @@ def sklearn_uses_brute(n: int, d: int, n_neighbors: int) -> bool:
 
 @dataclass
 class KnnPrep:
-    x: torch.Tensor          # original data [n, d] f32/f64
-    xt: torch.Tensor         # centred FP32 copy, tiled k-major (d_pad * ld floats)
+    x: torch.Tensor          # input data [n, d] f32/f64
+    perm: Optional[torch.Tensor]   # work order: work point i = input row perm[i] (None = identity)
+    xt: torch.Tensor         # centred FP32 copy in work order, tiled k-major (d_pad * ld floats)
     yn: torch.Tensor
     xcn: torch.Tensor
     xn64: torch.Tensor
     rmax2: torch.Tensor
+    tile_lo: Optional[torch.Tensor]
+    tile_hi: Optional[torch.Tensor]
     n: int
     d: int
     d_pad: int
     ld: int
 
 
-def knn_prepare(x: torch.Tensor) -> KnnPrep:
+def principal_direction(x: torch.Tensor, mean: torch.Tensor, iters: int = 12) -> torch.Tensor:
+    """Leading principal axis of the centred data by power iteration on X^T X (two passes over X
+    per step).  Only the *quality* of the pruning depends on it: any unit vector gives a valid bound."""
+    from . import _dist
+
+    n, d = x.shape
+    is64 = int(x.dtype == F64)
+    v = torch.full((d,), 1.0 / math.sqrt(d), dtype=F64, device=x.device)
+    proj = empty((n,), F64)
+    w = empty((d,), F64)
+    for _ in range(iters):
+        call("pb200_project_rows", x, is64, n, d, mean, v, proj)
+        call("pb200_weighted_col_sums", x, is64, n, d, mean, proj, w)
+        nrm = float(torch.linalg.vector_norm(w).item())
+        if not (nrm > 0.0):
+            break
+        v = w / nrm
+    v = (v / torch.linalg.vector_norm(v)) * (1.0 - 1e-12)       # |v| <= 1: projections never exceed distances
+    _dist.broadcast_(v)                                         # every rank must sort identically
+    return v.contiguous()
+
+
+def knn_prepare(x: torch.Tensor, prune: bool = True) -> KnnPrep:
+    """Mean-centre, sort the points along the leading principal axis (work order) and build the
+    candidate kernel's operands."""
+    from . import _device_core as dc_                      # argsort helper lives with the palantir stages
+
     n, d = x.shape
     if x.dtype not in (F32, F64):
         raise TypeError("kNN input must be float32 or float64")
     d_pad = max(16, round_up(d, 16))
     ld = round_up(n, 256)
-    xt = empty((d_pad, ld), F32)
+    is64 = int(x.dtype == F64)
+    mean = empty((d,), F64)
+    call("pb200_col_means", x, is64, n, d, mean)
+    perm = tile_lo = tile_hi = None
+    if prune and n > 512:
+        v = principal_direction(x, mean)
+        proj = empty((n,), F64)
+        call("pb200_project_rows", x, is64, n, d, mean, v, proj)
+        perm, _inv, _ = dc_.locality_order(proj.view(n, 1), want_sorted=False)
+        ntiles = ld // 128
+        tile_lo, tile_hi = empty((ntiles,), F64), empty((ntiles,), F64)
+        call("pb200_tile_intervals", proj, perm, n, ntiles, tile_lo, tile_hi)
+    xt = empty((d_pad * ld,), F32)
     yn = empty((ld,), F32)
     xcn = empty((n,), F64)
     xn64 = empty((n,), F64)
     rmax2 = empty((1,), F64)
-    col_sums = empty((d,), F64)
-    call("pb200_knn_prepare", x, int(x.dtype == F64), n, d, d_pad, ld, col_sums, xt, yn, xcn, xn64, rmax2)
-    return KnnPrep(x, xt, yn, xcn, xn64, rmax2, n, d, d_pad, ld)
+    call("pb200_knn_prepare", x, is64, n, d, d_pad, ld, mean, perm, xt, yn, xcn, xn64, rmax2)
+    return KnnPrep(x, perm, xt, yn, xcn, xn64, rmax2, tile_lo, tile_hi, n, d, d_pad, ld)
 
 
 def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
                  slack: int = 12) -> Tuple[torch.Tensor, torch.Tensor, dict]:
-    """k nearest references (self included) of query rows q0..q0+nq-1, sklearn brute
-    semantics.  Returns (idx int32 [nq,k], dist f64 [nq,k], stats).  q0 % 256 == 0."""
+    """k nearest references (self included) of WORK-order rows q0..q0+nq-1, sklearn brute semantics.
+    Returns (idx int32 [nq,k] of input-order indices, dist f64 [nq,k], stats); rows are in work order
+    (see knn_unpermute).  q0 % 256 == 0."""
     n, d = prep.n, prep.d
     nq = n - q0 if nq is None else nq
     if k > n:
@@ -133,6 +174,7 @@ def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
     stats = {"flagged": 0, "k_keep": 0}
     if nq == 0:
         return out_idx, out_dist, stats
+    is64 = int(prep.x.dtype == F64)
     if k > KNN_MAX_KEEP:
         # wider than the candidate buffers: exact FP64 brute force for every row
         rows = torch.arange(nq, dtype=I32, device=out_idx.device)
@@ -145,17 +187,19 @@ def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
     score = empty((nq, k_keep), F32)
     thr = empty((nq,), F32)
     lists = empty((round_up(nq, 256) * 64,), I64)
+    visited = zeros((1,), I64)
     with stage("knn_candidates"):
-        call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.xt, prep.ld, prep.yn, q0, nq, prep.d,
-             prep.d_pad, k_keep, lists, cand, score, thr)
+        call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.yn, prep.xcn, prep.tile_lo, prep.tile_hi, q0, nq,
+             prep.d, prep.d_pad, k_keep, lists, cand, score, thr, visited)
     del lists
     flag = empty((nq,), U8)
     n_flagged = empty((1,), I32)
     with stage("knn_rerank"):
-        call("pb200_knn_rerank_f64", prep.x, int(prep.x.dtype == F64), prep.xn64, prep.xcn, prep.rmax2, n, d,
-             q0, nq, cand, thr, k_keep, k, out_idx, out_dist, flag, n_flagged)
+        call("pb200_knn_rerank_f64", prep.x, is64, prep.perm, prep.xn64, prep.xcn, prep.rmax2, n, d, q0, nq, cand,
+             thr, k_keep, k, out_idx, out_dist, flag, n_flagged)
     nf = int(n_flagged.item())
     stats["flagged"] = nf
+    stats["tiles_visited_frac"] = float(visited.item()) / (max(1, (nq + 255) // 256) * (prep.ld // 128))
     if nf > 0:
         rows = empty((nq,), I32)
         counter = empty((1,), I32)
@@ -168,8 +212,17 @@ def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
 def _knn_exact_rows(prep: KnnPrep, rows, n_rows, q0, k, out_idx, out_dist):
     n_ctas = max(1, min(n_rows, 148))
     scratch = empty((n_ctas, prep.n), F64)
-    call("pb200_knn_exact_rows_f64", prep.x, int(prep.x.dtype == F64), prep.xn64, prep.n, prep.d, rows, n_rows,
-         q0, k, scratch, n_ctas, out_idx, out_dist)
+    call("pb200_knn_exact_rows_f64", prep.x, int(prep.x.dtype == F64), prep.perm, prep.xn64, prep.n, prep.d, rows,
+         n_rows, q0, k, scratch, n_ctas, out_idx, out_dist)
+
+
+def knn_unpermute(prep: KnnPrep, idx: torch.Tensor, dist: torch.Tensor):
+    """Full [n, k] tables with rows in work order -> rows in input order."""
+    if prep.perm is None:
+        return idx, dist
+    oi, od = torch.empty_like(idx), torch.empty_like(dist)
+    call("pb200_knn_unpermute", idx, dist, idx.shape[0], idx.shape[1], prep.perm, oi, od)
+    return oi, od
 
 
 def knn_direct(data: torch.Tensor, k: int, q0: int = 0, nq: Optional[int] = None,
@@ -190,16 +243,26 @@ def knn_direct(data: torch.Tensor, k: int, q0: int = 0, nq: Optional[int] = None
     return out_idx, out_dist
 
 
-def knn_like_sklearn(x: torch.Tensor, n_neighbors: int, q0: int = 0, nq: Optional[int] = None):
-    """Dispatch exactly as sklearn's algorithm='auto' would (see sklearn_uses_brute)."""
+def knn_like_sklearn(x: torch.Tensor, n_neighbors: int, shard: bool = False):
+    """Full self-including neighbour table, dispatching exactly as sklearn's algorithm='auto' would
+    (see sklearn_uses_brute).  With shard=True the query rows are split across the ranks of the
+    process group (contiguous blocks of the work order) and the row shards all-gathered."""
+    from . import _dist
+
     n, d = x.shape
+    q0, nq = _dist.row_shard(n, 256) if shard else (0, n)
     if sklearn_uses_brute(n, d, n_neighbors):
         prep = knn_prepare(x)
         idx, dist, stats = knn_expanded(prep, n_neighbors, q0, nq)
+        if shard:
+            idx, dist = _dist.allgather_rows(idx, dist, n, 256)
+        idx, dist = knn_unpermute(prep, idx, dist)
         stats["method"] = "expanded"
         return idx, dist, stats
     data = x if x.dtype == F64 else x.to(F64)
     idx, dist = knn_direct(data.contiguous(), n_neighbors, q0, nq)
+    if shard:
+        idx, dist = _dist.allgather_rows(idx, dist, n, 256)
     return idx, dist, {"method": "direct", "flagged": 0}
 
 

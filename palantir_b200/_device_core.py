@@ -76,13 +76,10 @@ def knn_table(data: torch.Tensor, knn: int):
     n = data.shape[0]
     if knn > n:
         raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {knn}, n_samples_fit = {n}")
-    q0, nq = _dist.row_shard(n, 256)
-    idx, dist, stats = dv.knn_like_sklearn(data, knn, q0, nq)
-    idx, dist = _dist.allgather_rows(idx, dist, n, 256)
-    return idx, dist, stats
+    return dv.knn_like_sklearn(data, knn, shard=True)
 
 
-def locality_order(dev: torch.Tensor):
+def locality_order(dev: torch.Tensor, want_sorted: bool = True):
     """Sort the cells along the first column.  Returns (perm, inv, sorted copy):
     sorted[i] = dev[perm[i]], inv[perm[i]] = i."""
     n, m = dev.shape
@@ -91,6 +88,8 @@ def locality_order(dev: torch.Tensor):
     scratch = empty((nbytes,), torch.uint8)
     perm, inv = empty((n,), I32), empty((n,), I32)
     call("pb200_argsort_col_f64", dev, n, m, 0, perm, inv, scratch, nbytes)
+    if not want_sorted:
+        return perm, inv, None
     out = empty((n, m), F64)
     call("pb200_permute_rows_f64", dev, n, m, perm, out)
     return perm, inv, out
@@ -147,10 +146,10 @@ def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, 
     lib = _native.load()
     n_ctas = lib.pb200_sssp_num_ctas(S)
     q = empty((n_ctas * 3 * n,), I32)
-    bits = empty((n_ctas * 2 * ((n + 31) // 32),), U32)
+    marks = empty((n_ctas * 2 * n,), I32)
     stats = zeros((S, 3), I64) if want_stats else None
     with stage("sssp"):
-        call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, bits, stats)
+        call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, marks, stats)
     return D, stats
 
 

@@ -11,20 +11,32 @@
 // k, and proves with an FP32 error bound that no excluded point can belong to the
 // true top-k (rows that cannot be proven are redone exactly in FP64).
 //
+// Work order and exact pruning.  The points are sorted along a unit direction v
+// (the leading principal axis, see _device.knn_prepare) and processed in that
+// order.  Since |v.(x - y)| <= |x - y|, a 128-point reference tile whose projection
+// interval lies further than g from the projection interval of a CTA's 256 query
+// rows can only contain points at distance >= g.  A CTA therefore walks the
+// reference tiles outwards from its own position (right, left, right, ...) and
+// drops a side for good once g^2 exceeds max_rows(thr_row + |x_row|^2), the largest
+// squared distance any of its rows could still accept.  Every dropped reference has
+// a true score above the row's threshold, which is what the re-rank certificate
+// needs.
+//
 // Layout: coordinates are stored tiled and k-major ("XT"): point i = 128*tile + il,
 // coordinate c = 16*kc + k lives at XT[((tile*KCH + kc)*16 + k)*128 + il], so the
 // 16 x 128 operand block of one (tile, kc) pipeline chunk is 8 KB of contiguous
 // memory and moves with ONE bulk copy; the last chunk of a tile carries only
 // k_tail = round_up(d - 16 (KCH-1), 4) coordinate rows.  The point count is padded
-// to a multiple of 256.  A CTA owns 256 query rows and streams every 128-point
-// reference tile through an 8-stage shared-memory ring filled by the TMA engine
-// (cp.async.bulk + mbarrier full/empty pairs; whichever warp reaches a chunk first
-// issues the copies for the chunk seven ahead, so no warp waits on a fixed producer).  16 consumer warps each own 16
-// query rows x 128 reference columns (8x8 register micro-tile per thread), so the
-// top-K lists of a row (L2-resident global scratch; only the per-row count and
-// threshold live in shared memory, which leaves room for an 8-deep ring) are only
-// ever touched by one warp and the selection needs no CTA-wide barrier.  One CTA per SM (512 threads, <=128 registers; a 17th,
-// dedicated producer warp would cap registers at 96).
+// to a multiple of 256.  A CTA owns 256 query rows and streams reference tiles
+// through an 8-stage shared-memory ring filled by the TMA engine (cp.async.bulk +
+// mbarrier full/empty pairs).  There is no producer warp and nobody blocks on an
+// "empty" barrier: at the top of every chunk each warp's lane 0 try-locks the
+// producer state and, if the next stage has been released, decides the next tile
+// and issues its copies.  16 warps each own 16 query rows x 128 reference columns
+// (8x8 register micro-tile per thread), so the top-K lists of a row (L2-resident
+// global scratch; only count and threshold live in shared memory) are only ever
+// touched by one warp and the selection needs no CTA-wide barrier.  One CTA per
+// SM (512 threads, 128 registers; a 17th warp would cap registers at 96).
 #include "common.cuh"
 
 namespace pb200 {
@@ -50,48 +62,109 @@ struct KnnSmem {
   KnnStage st[KNN_NST];
   int cnt[KNN_BM];
   float thr[KNN_BM];
+  float xcn[KNN_BM];            // |x_row|^2 rounded up (padding rows: -inf)
   uint64_t full[KNN_NST];
   uint64_t empty[KNN_NST];
-  int next_chunk;  // next pipeline chunk nobody has issued yet
+  int meta_tile[KNN_NST];       // reference tile of the chunk in this stage, -1 = end of stream
+  int meta_kc[KNN_NST];
+  float warp_bound[KNN_WARPS];  // max over the warp's rows of thr + |x|^2
+  // producer state (guarded by `lock`)
+  int lock;
+  int next_chunk;               // number of chunks issued so far
+  int cur_tile, cur_kc;
+  int left, right;
+  int l_done, r_done, turn, ended;
 };
 
 struct KnnParams {
-  const float* xtq;  // query coordinates, tiled k-major
-  const float* xtr;  // reference coordinates, tiled k-major
-  const float* yn;   // |y_j|^2 per reference (FP32, +inf on padding)
-  int q0;            // first query point (multiple of 256)
-  int nq;            // number of query rows handled by this launch
-  int n_ref_tiles;   // padded reference count / 128
-  int kch;           // d_pad / 16
-  int k_tail;        // coordinate rows in the last chunk of a tile (multiple of 4, <= 16)
+  const float* xt;        // coordinates, tiled k-major (queries are a row range of the same set)
+  const float* yn;        // |y_j|^2 per point (FP32, +inf on padding)
+  const double* xcn;      // |x_i|^2 per point (FP64, centred)
+  const double* tile_lo;  // projection interval of every 128-point tile (NULL: no pruning)
+  const double* tile_hi;
+  int q0;                 // first query point (multiple of 256)
+  int nq;                 // number of query rows handled by this launch
+  int n_tiles;            // padded point count / 128
+  int kch;                // d_pad / 16
+  int k_tail;             // coordinate rows in the last chunk of a tile (multiple of 4, <= 16)
   int k_keep;
-  unsigned long long* lists;  // [tiles*256][64] packed (score, index) candidate buffers (L2-resident scratch)
-  int* out_idx;      // [nq][k_keep]
-  float* out_score;  // [nq][k_keep]
-  float* out_thr;    // [nq]
+  unsigned long long* lists;  // [tiles*256][64] packed (score, index) candidate buffers
+  int* out_idx;           // [nq][k_keep]
+  float* out_score;       // [nq][k_keep]
+  float* out_thr;         // [nq]
+  unsigned long long* tiles_visited;  // optional counter
 };
 
 __device__ __forceinline__ unsigned long long pack_entry(float s, int idx) {
   return ((unsigned long long)f32_ordered(s) << 32) | (unsigned int)idx;
 }
 
-// Issue the bulk copies of pipeline chunk g into its (already released) stage; one thread.
-__device__ __noinline__ void knn_produce(KnnSmem* smp, const KnnParams* pp, int g, int qtile0) {
+// Producer step, called by one thread holding sm.lock: while the next stage is free, pick the
+// next (tile, kc) chunk -- walking the tiles outwards and pruning sides -- and issue its copies.
+__device__ __noinline__ void knn_produce(KnnSmem* smp, const KnnParams* pp, int qtile0, int max_issue) {
   KnnSmem& sm = *smp;
   const KnnParams& p = *pp;
   const int KCH = p.kch;
-  const int t = g / KCH, kc = g - t * KCH;
-  const int st = g % KNN_NST;
-  const bool last = (kc == KCH - 1);
-  const uint32_t blk_bytes = (uint32_t)(last ? p.k_tail : KNN_DK) * KNN_BN * 4u;
-  mbar_arrive_expect_tx(&sm.full[st], 3u * blk_bytes + (last ? KNN_BN * 4u : 0u));
-  const float* a0 = p.xtq + ((long long)qtile0 * KCH + kc) * KNN_BLOCK_FLOATS;
-  const float* a1 = a0 + (long long)KCH * KNN_BLOCK_FLOATS;
-  const float* br = p.xtr + ((long long)t * KCH + kc) * KNN_BLOCK_FLOATS;
-  bulk_g2s(&sm.st[st].a[0][0][0], a0, blk_bytes, &sm.full[st]);
-  bulk_g2s(&sm.st[st].a[1][0][0], a1, blk_bytes, &sm.full[st]);
-  bulk_g2s(&sm.st[st].b[0][0], br, blk_bytes, &sm.full[st]);
-  if (last) bulk_g2s(&sm.st[st].yn[0], p.yn + (long long)t * KNN_BN, KNN_BN * 4, &sm.full[st]);
+  for (int it = 0; it < max_issue; ++it) {
+    if (sm.ended) return;
+    const int g = sm.next_chunk;
+    const int st = g % KNN_NST;
+    if (!mbar_test(&sm.empty[st], (((uint32_t)(g / KNN_NST)) & 1u) ^ 1u)) return;
+    if (sm.cur_kc == 0) {
+      // choose the next reference tile
+      float bmax = sm.warp_bound[0];
+#pragma unroll
+      for (int w = 1; w < KNN_WARPS; ++w) bmax = fmaxf(bmax, sm.warp_bound[w]);
+      const double bound = (double)bmax;
+      int t = -1;
+      while (t < 0) {
+        if (sm.r_done && sm.l_done) break;
+        const bool go_right = (sm.turn == 0 && !sm.r_done) || sm.l_done;
+        sm.turn ^= 1;
+        if (go_right) {
+          if (sm.right >= p.n_tiles) { sm.r_done = 1; continue; }
+          if (p.tile_lo) {
+            double gap = p.tile_lo[sm.right] - p.tile_hi[qtile0 + 1];
+            gap = gap > 0.0 ? gap : 0.0;
+            if (gap * gap * (1.0 - 1e-9) > bound) { sm.r_done = 1; continue; }
+          }
+          t = sm.right++;
+        } else {
+          if (sm.left < 0) { sm.l_done = 1; continue; }
+          if (p.tile_lo) {
+            double gap = p.tile_lo[qtile0] - p.tile_hi[sm.left];
+            gap = gap > 0.0 ? gap : 0.0;
+            if (gap * gap * (1.0 - 1e-9) > bound) { sm.l_done = 1; continue; }
+          }
+          t = sm.left--;
+        }
+      }
+      if (t < 0) {
+        // end of stream: a data-less completion of this stage's "full" barrier
+        sm.meta_tile[st] = -1;
+        sm.ended = 1;
+        sm.next_chunk = g + 1;
+        mbar_arrive(&sm.full[st]);
+        return;
+      }
+      sm.cur_tile = t;
+    }
+    const int t = sm.cur_tile, kc = sm.cur_kc;
+    sm.meta_tile[st] = t;
+    sm.meta_kc[st] = kc;
+    const bool last = (kc == KCH - 1);
+    const uint32_t blk_bytes = (uint32_t)(last ? p.k_tail : KNN_DK) * KNN_BN * 4u;
+    mbar_arrive_expect_tx(&sm.full[st], 3u * blk_bytes + (last ? KNN_BN * 4u : 0u));
+    const float* a0 = p.xt + ((long long)qtile0 * KCH + kc) * KNN_BLOCK_FLOATS;
+    const float* a1 = a0 + (long long)KCH * KNN_BLOCK_FLOATS;
+    const float* br = p.xt + ((long long)t * KCH + kc) * KNN_BLOCK_FLOATS;
+    bulk_g2s(&sm.st[st].a[0][0][0], a0, blk_bytes, &sm.full[st]);
+    bulk_g2s(&sm.st[st].a[1][0][0], a1, blk_bytes, &sm.full[st]);
+    bulk_g2s(&sm.st[st].b[0][0], br, blk_bytes, &sm.full[st]);
+    if (last) bulk_g2s(&sm.st[st].yn[0], p.yn + (long long)t * KNN_BN, KNN_BN * 4, &sm.full[st]);
+    sm.cur_kc = last ? 0 : kc + 1;
+    sm.next_chunk = g + 1;
+  }
 }
 
 // Warp-collective: rank the (<= 64) buffered entries of a row (keys are unique because
@@ -130,93 +203,92 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
   const int lane = tid & 31;
   const int qbase = p.q0 + blockIdx.x * KNN_BM;  // first query point of this CTA
   const int row_local0 = blockIdx.x * KNN_BM;    // row in the output arrays
+  const int qtile0 = qbase / KNN_BN;
   unsigned long long* lists = p.lists + (long long)row_local0 * KNN_CAP;
 
   for (int r = tid; r < KNN_BM; r += KNN_THREADS) {
     sm.cnt[r] = 0;
     sm.thr[r] = INFINITY;
+    sm.xcn[r] = (row_local0 + r < p.nq) ? __double2float_ru(p.xcn[qbase + r]) : -INFINITY;
   }
+  if (tid < KNN_WARPS) sm.warp_bound[tid] = (row_local0 + tid * 16 < p.nq) ? INFINITY : -INFINITY;
   if (tid == 0) {
     for (int s = 0; s < KNN_NST; ++s) {
       mbar_init(&sm.full[s], 1);
       mbar_init(&sm.empty[s], KNN_WARPS);
     }
     fence_mbar_init();
+    sm.lock = 0; sm.next_chunk = 0; sm.cur_tile = 0; sm.cur_kc = 0;
+    sm.right = qtile0;
+    sm.left = qtile0 - 1;
+    sm.l_done = 0; sm.r_done = 0; sm.turn = 0; sm.ended = 0;
   }
   __syncthreads();
+  if (tid == 0) knn_produce(&sm, &p, qtile0, KNN_NST);
+  __syncthreads();
 
-  const int T = p.n_ref_tiles;
   const int KCH = p.kch;
-  const int total_chunks = T * KCH;
-  const int qtile0 = qbase / KNN_BN;
-  // Chunk g = t*KCH + kc lives in stage g % NST.  There is no producer warp and nobody
-  // ever blocks on an "empty" barrier: at the top of every chunk each warp's lane 0 tests
-  // (non-blocking) whether the stage of the next un-issued chunk has been released by all 16
-  // warps and, if so, claims it (CAS) and issues its bulk copies -- in practice the warp that
-  // released the stage last refills it a few cycles later.
-  if (tid == 0) {
-    int g = 0;
-    for (; g < KNN_NST && g < total_chunks; ++g) knn_produce(&sm, &p, g, qtile0);
-    sm.next_chunk = g;
-  }
-  __syncthreads();
-
   const int r0 = warp * 16 + (lane >> 4) * 8;  // first of this thread's 8 rows (CTA-local)
   const int a_off = (r0 >> 7) * KNN_BLOCK_FLOATS + (r0 & 127);
   const int c0 = (lane & 15) * 4;              // columns c0..c0+3 and 64+c0..64+c0+3
-  int stage = 0, gchunk = 0;
+  int stage = 0;
   uint32_t phase = 0;
+  unsigned int tiles_done = 0;
   float acc[8][8];
   float ynr[8];
 
-  for (int t = 0; t < T; ++t) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-    for (int kc = 0; kc < KCH; ++kc, ++gchunk) {
-      if (lane == 0) {
-        const int target = *(volatile int*)&sm.next_chunk;
-        if (target < total_chunks &&
-            mbar_test(&sm.empty[target % KNN_NST], (((uint32_t)(target / KNN_NST)) & 1u) ^ 1u) &&
-            atomicCAS(&sm.next_chunk, target, target + 1) == target)
-          knn_produce(&sm, &p, target, qtile0);
-      }
-      __syncwarp();
-      mbar_wait(&sm.full[stage], phase);
-      const float* As = &sm.st[stage].a[0][0][0] + a_off;
-      const float* Bs = &sm.st[stage].b[0][0] + c0;
-      const int klen = (kc == KCH - 1) ? p.k_tail : KNN_DK;
-#pragma unroll 1
-      for (int k0 = 0; k0 < klen; k0 += 4) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int k = k0 + kk;
-          const float4 a0 = *reinterpret_cast<const float4*>(As + k * KNN_BN);
-          const float4 a1 = *reinterpret_cast<const float4*>(As + k * KNN_BN + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN);
-          const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN + 64);
-          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-      }
-      if (kc == KCH - 1) {
-        const float4 y0 = *reinterpret_cast<const float4*>(&sm.st[stage].yn[c0]);
-        const float4 y1 = *reinterpret_cast<const float4*>(&sm.st[stage].yn[64 + c0]);
-        ynr[0] = y0.x; ynr[1] = y0.y; ynr[2] = y0.z; ynr[3] = y0.w;
-        ynr[4] = y1.x; ynr[5] = y1.y; ynr[6] = y1.z; ynr[7] = y1.w;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.empty[stage]);
-      if (++stage == KNN_NST) { stage = 0; phase ^= 1u; }
+  for (;;) {
+    if (lane == 0 && !*(volatile int*)&sm.ended && atomicCAS(&sm.lock, 0, 1) == 0) {
+      __threadfence_block();
+      knn_produce(&sm, &p, qtile0, 2);
+      __threadfence_block();
+      atomicExch(&sm.lock, 0);
     }
+    __syncwarp();
+    mbar_wait(&sm.full[stage], phase);
+    const int t = sm.meta_tile[stage];
+    if (t < 0) break;  // end of stream (every warp sees it in the same stage)
+    const int kc = sm.meta_kc[stage];
+    if (kc == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    }
+    const float* As = &sm.st[stage].a[0][0][0] + a_off;
+    const float* Bs = &sm.st[stage].b[0][0] + c0;
+    const bool last = (kc == KCH - 1);
+    const int klen = last ? p.k_tail : KNN_DK;
+#pragma unroll 1
+    for (int k0 = 0; k0 < klen; k0 += 4) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = k0 + kk;
+        const float4 a0 = *reinterpret_cast<const float4*>(As + k * KNN_BN);
+        const float4 a1 = *reinterpret_cast<const float4*>(As + k * KNN_BN + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN);
+        const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * KNN_BN + 64);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+    if (last) {
+      const float4 y0 = *reinterpret_cast<const float4*>(&sm.st[stage].yn[c0]);
+      const float4 y1 = *reinterpret_cast<const float4*>(&sm.st[stage].yn[64 + c0]);
+      ynr[0] = y0.x; ynr[1] = y0.y; ynr[2] = y0.z; ynr[3] = y0.w;
+      ynr[4] = y1.x; ynr[5] = y1.y; ynr[6] = y1.z; ynr[7] = y1.w;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.empty[stage]);
+    if (++stage == KNN_NST) { stage = 0; phase ^= 1u; }
+    if (!last) continue;
 
     // ---- selection: fast reject against the per-row threshold ----
+    ++tiles_done;
     bool hit = false;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -228,6 +300,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
     }
     if (__any_sync(0xffffffffu, hit)) {
       const int colbase = t * KNN_BN;
+      bool compacted = false;
       for (;;) {
         bool fail = false;
 #pragma unroll
@@ -253,9 +326,21 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
         __syncwarp();
         for (int rr = 0; rr < 16; ++rr) {
           const int row = warp * 16 + rr;
-          if (sm.cnt[row] >= KNN_HIGH) knn_compact_row(&sm, lists + row * KNN_CAP, row, p.k_keep, lane);
+          if (sm.cnt[row] >= KNN_HIGH) {
+            knn_compact_row(&sm, lists + row * KNN_CAP, row, p.k_keep, lane);
+            compacted = true;
+          }
         }
         if (!__any_sync(0xffffffffu, fail)) break;
+      }
+      if (compacted) {
+        // refresh this warp's pruning bound: max over its rows of thr + |x|^2 (rounded up)
+        float b = -INFINITY;
+        if (lane < 16 && sm.xcn[warp * 16 + lane] != -INFINITY)
+          b = __fadd_ru(sm.thr[warp * 16 + lane], sm.xcn[warp * 16 + lane]);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        if (lane == 0) sm.warp_bound[warp] = b;
       }
     }
   }
@@ -296,24 +381,28 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
     }
     if (lane == 0) p.out_thr[grow] = thr_out;
   }
+  if (tid == 0 && p.tiles_visited) atomicAdd(p.tiles_visited, (unsigned long long)tiles_done);
 }
 
 // ----------------------------------------------------------------------------
-// Preparation: column means, centred FP32 k-major copy, norms.
+// Preparation: column means, principal direction, centred FP32 tiled copy, norms.
 // ----------------------------------------------------------------------------
 template <typename T>
-__global__ void col_sums_kernel(const T* __restrict__ x, long long n, int d, double* __restrict__ sums) {
-  // block (32, 8); thread handles columns tx, tx+32, ... (<= 32 slots => d <= 1024)
+__global__ void col_sums_kernel(const T* __restrict__ x, long long n, int d, const double* __restrict__ wrow,
+                                const double* __restrict__ mean, double* __restrict__ sums) {
+  // block (32, 8); thread handles columns tx, tx+32, ... (<= 32 slots => d <= 1024).
+  // wrow == NULL: sums[c] += x[r][c];  else sums[c] += wrow[r] * (x[r][c] - mean[c])
   double loc[32];
 #pragma unroll
   for (int s = 0; s < 32; ++s) loc[s] = 0.0;
   const int tx = threadIdx.x, ty = threadIdx.y;
   for (long long r = (long long)blockIdx.x * 8 + ty; r < n; r += (long long)gridDim.x * 8) {
     const T* row = x + r * d;
+    const double w = wrow ? wrow[r] : 1.0;
 #pragma unroll
     for (int s = 0; s < 32; ++s) {
       const int c = tx + 32 * s;
-      if (c < d) loc[s] += (double)row[c];
+      if (c < d) loc[s] += wrow ? w * ((double)row[c] - mean[c]) : (double)row[c];
     }
   }
 #pragma unroll
@@ -323,16 +412,30 @@ __global__ void col_sums_kernel(const T* __restrict__ x, long long n, int d, dou
   }
 }
 
-// One block = 32 points.  Writes the tiled k-major copy (see the header comment)
-// xt[((i/128 * KCH + c/16)*16 + c%16)*128 + i%128] = (float)(x[i][c] - mean[c]) (0 on
+// proj[r] = sum_c (float)(x[r][c] - mean[c]) * v[c]   (one warp per row, FP64 accumulate)
+template <typename T>
+__global__ void project_rows_kernel(const T* __restrict__ x, long long n, int d, const double* __restrict__ mean,
+                                    const double* __restrict__ v, double* __restrict__ proj) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= n) return;
+  double s = 0.0;
+  for (int c = lane; c < d; c += 32) s = fma((double)(float)((double)x[r * d + c] - mean[c]), v[c], s);
+  s = warp_sum(s);
+  if (lane == 0) proj[r] = s;
+}
+
+// One block = 32 points (in WORK order: point i is source row perm[i], or i when perm == NULL).
+// Writes the tiled k-major copy (see the header comment)
+// xt[((i/128 * KCH + c/16)*16 + c%16)*128 + i%128] = (float)(x[src][c] - mean[c]) (0 on
 // padding), yn[i] = (float)sum_c xt^2 (+inf on padding rows), xcn[i] = the same
-// sum in FP64, xn64[i] = sum_c x[i][c]^2 in FP64 on the ORIGINAL values (the
+// sum in FP64, xn64[i] = sum_c x[src][c]^2 in FP64 on the ORIGINAL values (the
 // reference's row norm), and the running max of xcn in *rmax2_bits.
 template <typename T>
 __global__ void knn_prep_kernel(const T* __restrict__ x, long long n, int d, int d_pad, long long ld,
-                                const double* __restrict__ sums, float* __restrict__ xt,
-                                float* __restrict__ yn, double* __restrict__ xcn, double* __restrict__ xn64,
-                                unsigned long long* __restrict__ rmax2_bits) {
+                                const double* __restrict__ mean, const int* __restrict__ perm,
+                                float* __restrict__ xt, float* __restrict__ yn, double* __restrict__ xcn,
+                                double* __restrict__ xn64, unsigned long long* __restrict__ rmax2_bits) {
   __shared__ float tile[32][33];
   __shared__ double part_c[8][32];
   __shared__ double part_o[8][32];
@@ -340,17 +443,22 @@ __global__ void knn_prep_kernel(const T* __restrict__ x, long long n, int d, int
   const long long i0 = (long long)blockIdx.x * 32;
   double accc[4] = {0, 0, 0, 0};  // rows ty, ty+8, ty+16, ty+24 (partial over this thread's columns)
   double acco[4] = {0, 0, 0, 0};
-  const double inv_n = 1.0 / (double)n;
+  long long src[4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const long long i = i0 + ty + 8 * rr;
+    src[rr] = i < n ? (perm ? (long long)perm[i] : i) : -1;
+  }
+  const long long kch = d_pad / KNN_DK;
   for (int cb = 0; cb < d_pad; cb += 32) {
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       const int r = ty + 8 * rr;
-      const long long i = i0 + r;
       const int c = cb + tx;
       float v = 0.f;
-      if (i < n && c < d) {
-        const double orig = (double)x[i * d + c];
-        v = (float)(orig - sums[c] * inv_n);
+      if (src[rr] >= 0 && c < d) {
+        const double orig = (double)x[src[rr] * d + c];
+        v = (float)(orig - mean[c]);
         acco[rr] = fma(orig, orig, acco[rr]);
         accc[rr] = fma((double)v, (double)v, accc[rr]);
       }
@@ -362,13 +470,11 @@ __global__ void knn_prep_kernel(const T* __restrict__ x, long long n, int d, int
       const int c = cb + ty + 8 * rr;
       if (c < d_pad) {
         const long long i = i0 + tx;
-        const long long kch = d_pad / KNN_DK;
         xt[(((i >> 7) * kch + (c >> 4)) * KNN_DK + (c & 15)) * KNN_BN + (i & 127)] = tile[tx][ty + 8 * rr];
       }
     }
     __syncthreads();
   }
-  // reduce the per-thread partial norms across tx (columns) for each of the 4 rows
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
     const double sc = warp_sum(accc[rr]);
@@ -390,6 +496,24 @@ __global__ void knn_prep_kernel(const T* __restrict__ x, long long n, int d, int
       yn[i] = INFINITY;
     }
   }
+}
+
+// interval [lo, hi] of the (sorted) projections of each 128-point tile
+__global__ void tile_intervals_kernel(const double* __restrict__ proj, const int* __restrict__ perm, long long n,
+                                      long long ntiles, double* __restrict__ lo, double* __restrict__ hi) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const long long a = t * KNN_BN;
+  long long b = a + KNN_BN - 1;
+  if (a >= n) { lo[t] = INFINITY; hi[t] = INFINITY; return; }   // pure padding tile: pruned at once
+  if (b > n - 1) b = n - 1;
+  lo[t] = proj[perm[a]];
+  hi[t] = proj[perm[b]];
+}
+
+__global__ void scale_to_mean_kernel(double* v, int d, double inv_n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < d) v[c] *= inv_n;
 }
 
 // Pure FFMA throughput probe (roofline denominator for the kNN stage).
@@ -414,53 +538,98 @@ using namespace pb200;
 
 extern "C" {
 
-int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, long long ld, double* col_sums,
-                      float* xt, float* yn, double* xcn, double* xn64, double* rmax2, void* stream) {
+// mean[c] = column means of x (d doubles).
+int pb200_col_means(const void* x, int is_f64, long long n, int d, double* mean, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (d > 1024 || d_pad % KNN_DK != 0 || d_pad < d || ld % KNN_BM != 0 || ld < n) {
-    set_error_msg("pb200_knn_prepare: need d <= 1024, d_pad % 16 == 0, ld % 256 == 0, ld >= n");
-    return -1;
-  }
-  PB_CHECK(cudaMemsetAsync(col_sums, 0, sizeof(double) * d, st));
-  PB_CHECK(cudaMemsetAsync(rmax2, 0, sizeof(double), st));
+  if (d > 1024) { set_error_msg("pb200_col_means: need d <= 1024"); return -1; }
+  PB_CHECK(cudaMemsetAsync(mean, 0, sizeof(double) * d, st));
   const int gb = (int)((n + 7) / 8 < 4 * kSMs ? (n + 7) / 8 : 4 * kSMs);
   dim3 blk(32, 8);
-  if (is_f64) col_sums_kernel<double><<<gb, blk, 0, st>>>((const double*)x, n, d, col_sums);
-  else        col_sums_kernel<float><<<gb, blk, 0, st>>>((const float*)x, n, d, col_sums);
+  if (is_f64) col_sums_kernel<double><<<gb, blk, 0, st>>>((const double*)x, n, d, nullptr, nullptr, mean);
+  else        col_sums_kernel<float><<<gb, blk, 0, st>>>((const float*)x, n, d, nullptr, nullptr, mean);
   PB_CHECK_LAUNCH("col_sums_kernel");
+  scale_to_mean_kernel<<<div_up(d, 256), 256, 0, st>>>(mean, d, 1.0 / (double)n);
+  PB_CHECK_LAUNCH("scale_to_mean_kernel");
+  return 0;
+}
+
+// proj[r] = (x[r] - mean) . v with the centred values rounded to FP32 first (the points the
+// candidate kernel actually works on).
+int pb200_project_rows(const void* x, int is_f64, long long n, int d, const double* mean, const double* v,
+                       double* proj, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (is_f64) project_rows_kernel<double><<<div_up(n, 8), 256, 0, st>>>((const double*)x, n, d, mean, v, proj);
+  else        project_rows_kernel<float><<<div_up(n, 8), 256, 0, st>>>((const float*)x, n, d, mean, v, proj);
+  PB_CHECK_LAUNCH("project_rows_kernel");
+  return 0;
+}
+
+// out[c] = sum_r w[r] * (x[r][c] - mean[c])   (one step of the covariance power iteration)
+int pb200_weighted_col_sums(const void* x, int is_f64, long long n, int d, const double* mean, const double* w,
+                            double* out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d > 1024) { set_error_msg("pb200_weighted_col_sums: need d <= 1024"); return -1; }
+  PB_CHECK(cudaMemsetAsync(out, 0, sizeof(double) * d, st));
+  const int gb = (int)((n + 7) / 8 < 4 * kSMs ? (n + 7) / 8 : 4 * kSMs);
+  dim3 blk(32, 8);
+  if (is_f64) col_sums_kernel<double><<<gb, blk, 0, st>>>((const double*)x, n, d, w, mean, out);
+  else        col_sums_kernel<float><<<gb, blk, 0, st>>>((const float*)x, n, d, w, mean, out);
+  PB_CHECK_LAUNCH("col_sums_kernel(weighted)");
+  return 0;
+}
+
+int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, long long ld, const double* mean,
+                      const int* perm, float* xt, float* yn, double* xcn, double* xn64, double* rmax2,
+                      void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d > 1024 || d_pad % KNN_DK != 0 || d_pad < d || d_pad - d >= KNN_DK || ld % KNN_BM != 0 || ld < n) {
+    set_error_msg("pb200_knn_prepare: need d <= 1024, d_pad % 16 == 0, d_pad - d < 16, ld % 256 == 0, ld >= n");
+    return -1;
+  }
+  PB_CHECK(cudaMemsetAsync(rmax2, 0, sizeof(double), st));
+  dim3 blk(32, 8);
   const int nb = (int)(ld / 32);
   if (is_f64)
-    knn_prep_kernel<double><<<nb, blk, 0, st>>>((const double*)x, n, d, d_pad, ld, col_sums, xt, yn, xcn, xn64,
+    knn_prep_kernel<double><<<nb, blk, 0, st>>>((const double*)x, n, d, d_pad, ld, mean, perm, xt, yn, xcn, xn64,
                                                  (unsigned long long*)rmax2);
   else
-    knn_prep_kernel<float><<<nb, blk, 0, st>>>((const float*)x, n, d, d_pad, ld, col_sums, xt, yn, xcn, xn64,
+    knn_prep_kernel<float><<<nb, blk, 0, st>>>((const float*)x, n, d, d_pad, ld, mean, perm, xt, yn, xcn, xn64,
                                                 (unsigned long long*)rmax2);
   PB_CHECK_LAUNCH("knn_prep_kernel");
   return 0;
 }
 
-int pb200_knn_candidates_f32(const float* xtq, long long nq_pad, const float* xtr, long long n_ref_pad,
-                             const float* yn, int q0, int nq, int d, int d_pad, int k_keep,
-                             unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
-                             void* stream) {
+// lo[t], hi[t] = projection of the first / last point of work-order tile t (proj indexed by source row)
+int pb200_tile_intervals(const double* proj, const int* perm, long long n, long long ntiles, double* lo, double* hi,
+                         void* stream) {
+  tile_intervals_kernel<<<div_up(ntiles, 256), 256, 0, (cudaStream_t)stream>>>(proj, perm, n, ntiles, lo, hi);
+  PB_CHECK_LAUNCH("tile_intervals_kernel");
+  return 0;
+}
+
+int pb200_knn_candidates_f32(const float* xt, long long n_pad, const float* yn, const double* xcn,
+                             const double* tile_lo, const double* tile_hi, int q0, int nq, int d, int d_pad,
+                             int k_keep, unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
+                             unsigned long long* tiles_visited, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (k_keep < 1 || k_keep > KNN_MAX_KEEP || q0 % KNN_BM != 0 || n_ref_pad % KNN_BM != 0 ||
-      nq_pad % KNN_BM != 0 || d_pad % KNN_DK != 0 || d_pad < KNN_DK || d < 1 || d > d_pad ||
-      d_pad - d >= KNN_DK) {
+  if (k_keep < 1 || k_keep > KNN_MAX_KEEP || q0 % KNN_BM != 0 || n_pad % KNN_BM != 0 || d_pad % KNN_DK != 0 ||
+      d_pad < KNN_DK || d < 1 || d > d_pad || d_pad - d >= KNN_DK) {
     set_error_msg("pb200_knn_candidates_f32: bad k_keep / alignment");
     return -1;
   }
   if (nq <= 0) return 0;
   const int tiles = div_up(nq, KNN_BM);
-  if ((long long)q0 + (long long)tiles * KNN_BM > nq_pad) {
-    set_error_msg("pb200_knn_candidates_f32: query tiles exceed the padded query count");
+  if ((long long)q0 + (long long)tiles * KNN_BM > n_pad) {
+    set_error_msg("pb200_knn_candidates_f32: query tiles exceed the padded point count");
     return -1;
   }
   KnnParams p;
-  p.xtq = xtq; p.xtr = xtr; p.yn = yn;
-  p.q0 = q0; p.nq = nq; p.n_ref_tiles = (int)(n_ref_pad / KNN_BN); p.kch = d_pad / KNN_DK; p.k_keep = k_keep;
+  p.xt = xt; p.yn = yn; p.xcn = xcn; p.tile_lo = tile_lo; p.tile_hi = tile_hi;
+  p.q0 = q0; p.nq = nq; p.n_tiles = (int)(n_pad / KNN_BN);
+  p.kch = d_pad / KNN_DK; p.k_keep = k_keep;
   p.k_tail = ((d - (d_pad - KNN_DK)) + 3) / 4 * 4;
   p.lists = lists; p.out_idx = out_idx; p.out_score = out_score; p.out_thr = out_thr;
+  p.tiles_visited = tiles_visited;
   static bool attr_set = false;
   const int smem = (int)sizeof(KnnSmem);
   if (!attr_set) {

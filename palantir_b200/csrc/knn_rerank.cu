@@ -28,17 +28,19 @@ __device__ __forceinline__ double dist_out<float>(double d2) {
 // One warp per query row; lane handles candidates lane and lane+32 (K <= 64).
 template <typename T>
 __global__ void __launch_bounds__(128) knn_rerank_kernel(
-    const T* __restrict__ x, const double* __restrict__ xn64, const double* __restrict__ xcn,
-    const double* __restrict__ rmax2, long long n, int d, int q0, int nq, const int* __restrict__ cand,
+    const T* __restrict__ x, const int* __restrict__ perm, const double* __restrict__ xn64,
+    const double* __restrict__ xcn, const double* __restrict__ rmax2, long long n, int d, int q0, int nq,
+    const int* __restrict__ cand,
     const float* __restrict__ thr32, int kk, int k, int* __restrict__ out_idx, double* __restrict__ out_dist,
     unsigned char* __restrict__ flag, int* __restrict__ n_flagged) {
   extern __shared__ double xs[];  // [4][d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * 4 + warp;
   if (q >= nq) return;
-  const long long i = (long long)q0 + q;
+  const long long i = (long long)q0 + q;            // work-order position of the query
+  const long long isrc = perm ? perm[i] : i;        // its row in x
   double* xi = xs + (size_t)warp * d;
-  for (int c = lane; c < d; c += 32) xi[c] = (double)x[i * d + c];
+  for (int c = lane; c < d; c += 32) xi[c] = (double)x[isrc * d + c];
   __syncwarp();
   const double xni = xn64[i];
 
@@ -50,11 +52,13 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(
     int j = slot < kk ? cand[(long long)q * kk + slot] : -1;
     double d2 = INFINITY;
     if (j >= 0) {
-      const T* y = x + (long long)j * d;
+      const int jsrc = perm ? perm[j] : j;
+      const T* y = x + (long long)jsrc * d;
       double dot = 0.0;
       for (int c = 0; c < d; ++c) dot = fma(xi[c], (double)y[c], dot);
       d2 = (-2.0 * dot + xni) + xn64[j];
       d2 = d2 > 0.0 ? d2 : 0.0;
+      j = jsrc;                                      // report / tie-break on the original index
     } else {
       j = 0x7fffffff;
     }
@@ -103,8 +107,8 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(
 // of block-wide lexicographic arg-min.
 template <typename T>
 __global__ void __launch_bounds__(512) knn_exact_rows_kernel(
-    const T* __restrict__ x, const double* __restrict__ xn64, long long n, int d, const int* __restrict__ rows,
-    int n_rows, int q0, int k, double* __restrict__ scratch, int* __restrict__ out_idx,
+    const T* __restrict__ x, const int* __restrict__ perm, const double* __restrict__ xn64, long long n, int d,
+    const int* __restrict__ rows, int n_rows, int q0, int k, double* __restrict__ scratch, int* __restrict__ out_idx,
     double* __restrict__ out_dist) {
   extern __shared__ double xs[];  // [d]
   __shared__ double red_d[16];
@@ -116,12 +120,13 @@ __global__ void __launch_bounds__(512) knn_exact_rows_kernel(
   for (int rr = blockIdx.x; rr < n_rows; rr += gridDim.x) {
     const int q = rows[rr];              // row index relative to q0
     const long long i = (long long)q0 + q;
+    const long long isrc = perm ? perm[i] : i;
     __syncthreads();
-    for (int c = tid; c < d; c += 512) xs[c] = (double)x[i * d + c];
+    for (int c = tid; c < d; c += 512) xs[c] = (double)x[isrc * d + c];
     __syncthreads();
     const double xni = xn64[i];
     for (long long j = tid; j < n; j += 512) {
-      const T* y = x + j * d;
+      const T* y = x + (perm ? (long long)perm[j] : j) * d;
       double dot = 0.0;
       for (int c = 0; c < d; ++c) dot = fma(xs[c], (double)y[c], dot);
       double d2 = (-2.0 * dot + xni) + xn64[j];
@@ -136,7 +141,8 @@ __global__ void __launch_bounds__(512) knn_exact_rows_kernel(
       int bi = 0x7fffffff;
       for (long long j = tid; j < n; j += 512) {
         const double v = sc[j];
-        if (key_less(ld, li, v, (int)j) && key_less(v, (int)j, bd, bi)) { bd = v; bi = (int)j; }
+        const int jo = perm ? perm[j] : (int)j;      // rank and report by the original index
+        if (key_less(ld, li, v, jo) && key_less(v, jo, bd, bi)) { bd = v; bi = jo; }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -174,16 +180,28 @@ __global__ void compact_flags_kernel(const unsigned char* __restrict__ flag, int
   if (q < nq && flag[q]) rows[atomicAdd(counter, 1)] = q;
 }
 
+// out_*[perm[i]][:] = in_*[i][:]  (neighbour table rows from work order back to input order)
+__global__ void knn_unpermute_kernel(const int* __restrict__ idx, const double* __restrict__ dist, long long n,
+                                     int k, const int* __restrict__ perm, int* __restrict__ oidx,
+                                     double* __restrict__ odist) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * k) return;
+  const long long i = e / k;
+  const long long o = (long long)perm[i] * k + (e - i * k);
+  oidx[o] = idx[e];
+  odist[o] = dist[e];
+}
+
 }  // namespace pb200
 
 using namespace pb200;
 
 extern "C" {
 
-int pb200_knn_rerank_f64(const void* x, int is_f64, const double* xn64, const double* xcn, const double* rmax2,
-                         long long n, int d, int q0, int nq, const int* cand, const float* thr32, int k_keep,
-                         int k, int* out_idx, double* out_dist, unsigned char* flag, int* n_flagged,
-                         void* stream) {
+int pb200_knn_rerank_f64(const void* x, int is_f64, const int* perm, const double* xn64, const double* xcn,
+                         const double* rmax2, long long n, int d, int q0, int nq, const int* cand,
+                         const float* thr32, int k_keep, int k, int* out_idx, double* out_dist,
+                         unsigned char* flag, int* n_flagged, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (k_keep > 64 || k > k_keep || k < 1) {
     set_error_msg("pb200_knn_rerank_f64: need 1 <= k <= k_keep <= 64");
@@ -194,11 +212,13 @@ int pb200_knn_rerank_f64(const void* x, int is_f64, const double* xn64, const do
   const int blocks = div_up(nq, 4);
   const size_t smem = sizeof(double) * 4 * (size_t)d;
   if (is_f64)
-    knn_rerank_kernel<double><<<blocks, 128, smem, st>>>((const double*)x, xn64, xcn, rmax2, n, d, q0, nq, cand,
-                                                          thr32, k_keep, k, out_idx, out_dist, flag, n_flagged);
+    knn_rerank_kernel<double><<<blocks, 128, smem, st>>>((const double*)x, perm, xn64, xcn, rmax2, n, d, q0, nq,
+                                                          cand, thr32, k_keep, k, out_idx, out_dist, flag,
+                                                          n_flagged);
   else
-    knn_rerank_kernel<float><<<blocks, 128, smem, st>>>((const float*)x, xn64, xcn, rmax2, n, d, q0, nq, cand,
-                                                         thr32, k_keep, k, out_idx, out_dist, flag, n_flagged);
+    knn_rerank_kernel<float><<<blocks, 128, smem, st>>>((const float*)x, perm, xn64, xcn, rmax2, n, d, q0, nq,
+                                                         cand, thr32, k_keep, k, out_idx, out_dist, flag,
+                                                         n_flagged);
   PB_CHECK_LAUNCH("knn_rerank_kernel");
   return 0;
 }
@@ -214,21 +234,29 @@ int pb200_knn_flagged_rows(const unsigned char* flag, int nq, int* rows_out, int
 }
 
 // scratch: n_ctas * n doubles.  rows are relative to q0 (like out_idx/out_dist rows).
-int pb200_knn_exact_rows_f64(const void* x, int is_f64, const double* xn64, long long n, int d, const int* rows,
-                             int n_rows, int q0, int k, double* scratch, int n_ctas, int* out_idx,
-                             double* out_dist, void* stream) {
+int pb200_knn_exact_rows_f64(const void* x, int is_f64, const int* perm, const double* xn64, long long n, int d,
+                             const int* rows, int n_rows, int q0, int k, double* scratch, int n_ctas,
+                             int* out_idx, double* out_dist, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (n_rows <= 0) return 0;
   if (n_ctas < 1) { set_error_msg("pb200_knn_exact_rows_f64: n_ctas < 1"); return -1; }
   const int grid = n_rows < n_ctas ? n_rows : n_ctas;
   const size_t smem = sizeof(double) * (size_t)d;
   if (is_f64)
-    knn_exact_rows_kernel<double><<<grid, 512, smem, st>>>((const double*)x, xn64, n, d, rows, n_rows, q0, k,
-                                                            scratch, out_idx, out_dist);
+    knn_exact_rows_kernel<double><<<grid, 512, smem, st>>>((const double*)x, perm, xn64, n, d, rows, n_rows, q0,
+                                                            k, scratch, out_idx, out_dist);
   else
-    knn_exact_rows_kernel<float><<<grid, 512, smem, st>>>((const float*)x, xn64, n, d, rows, n_rows, q0, k,
-                                                           scratch, out_idx, out_dist);
+    knn_exact_rows_kernel<float><<<grid, 512, smem, st>>>((const float*)x, perm, xn64, n, d, rows, n_rows, q0,
+                                                           k, scratch, out_idx, out_dist);
   PB_CHECK_LAUNCH("knn_exact_rows_kernel");
+  return 0;
+}
+
+int pb200_knn_unpermute(const int* idx, const double* dist, long long n, int k, const int* perm, int* out_idx,
+                        double* out_dist, void* stream) {
+  knn_unpermute_kernel<<<div_up(n * k, 256), 256, 0, (cudaStream_t)stream>>>(idx, dist, n, k, perm, out_idx,
+                                                                            out_dist);
+  PB_CHECK_LAUNCH("knn_unpermute_kernel");
   return 0;
 }
 

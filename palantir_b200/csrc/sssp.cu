@@ -7,12 +7,15 @@
 // One CTA per source (persistent CTAs loop over the sources), near/far
 // delta-stepping: distances live in the output row D[s][:] (FP64, atomicMin on the
 // bit pattern), the "near" work lists and the "far" pile are per-CTA global buffers
-// that stay L2-resident, membership bitmaps de-duplicate pushes, and only
-// __syncthreads separates rounds -- no grid-wide synchronisation, no host round
-// trips.  The graph on which Palantir runs this is long and thin (shortest-path
-// trees thousands of hops deep), so the design optimises the
-// per-round latency of many independent sources rather than the width of one
-// frontier.
+// that stay L2-resident, epoch-stamped marks de-duplicate pushes without any
+// clearing pass, and only __syncthreads separates rounds -- no grid-wide
+// synchronisation, no host round trips.  The graph Palantir runs this on is long and
+// thin (shortest-path trees tens of thousands of hops deep at 1 M cells, SURVEY.md
+// 7b-2), so a source needs ~3*10^4 rounds of a few dozen vertices each: the kernel is
+// bound by the latency of one round, not by bandwidth.  A round is therefore flat:
+// the frontier's (dist, row extent) are fetched by one thread per vertex, a block
+// scan of the degrees assigns ONE ARC PER THREAD, and all arcs of the round are
+// relaxed in a single wave of dependent loads.
 //
 // Any label-correcting order converges to the same fixed point as Dijkstra,
 // dist[v] = min_u fl(dist[u] + w_uv), because FP64 addition is monotone; the
@@ -22,90 +25,116 @@
 namespace pb200 {
 
 constexpr int SSSP_THREADS = 512;
-
-__device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
-
-struct SsspScratch {
-  int* qa;             // near list (current round)
-  int* qb;             // near list (next round)
-  int* far;            // far pile
-  unsigned int* bnear; // bitmap: vertex is in qb
-  unsigned int* bfar;  // bitmap: vertex is in far
-};
+constexpr int SSSP_WARPS = SSSP_THREADS / 32;
 
 __global__ void __launch_bounds__(SSSP_THREADS) sssp_kernel(
     const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ wts, int n,
     const long long* __restrict__ sources, int n_sources, double delta, double* __restrict__ D,
-    int* __restrict__ q_all, unsigned int* __restrict__ bits_all, long long* __restrict__ stats) {
-  __shared__ int s_cnt_next, s_cnt_far, s_cnt_near;
+    int* __restrict__ q_all, int* __restrict__ marks_all, long long* __restrict__ stats) {
+  __shared__ int s_cnt[2];
+  __shared__ int s_cnt_far;
   __shared__ double s_thr;
-  __shared__ double s_red[SSSP_THREADS / 32];
-  __shared__ int s_scan[SSSP_THREADS / 32];
+  __shared__ double s_red[SSSP_WARPS];
+  __shared__ int s_wtot[SSSP_WARPS];
+  __shared__ int s_wtot2[SSSP_WARPS];
   __shared__ int s_base_keep, s_base_near;
+  // frontier chunk staged in shared memory
+  __shared__ double c_du[SSSP_THREADS];
+  __shared__ int c_beg[SSSP_THREADS];
+  __shared__ int c_pre[SSSP_THREADS + 1];  // exclusive prefix of degrees
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = SSSP_THREADS / 32;
-  const int nwords = (n + 31) >> 5;
-  int* qa = q_all + (size_t)blockIdx.x * 3 * (size_t)n;
-  int* qb = qa + n;
-  int* far = qb + n;
-  unsigned int* bnear = bits_all + (size_t)blockIdx.x * 2 * (size_t)nwords;
-  unsigned int* bfar = bnear + nwords;
+  int* qbuf[2];
+  qbuf[0] = q_all + (size_t)blockIdx.x * 3 * (size_t)n;
+  qbuf[1] = qbuf[0] + n;
+  int* far = qbuf[1] + n;
+  int* mnear = marks_all + (size_t)blockIdx.x * 2 * (size_t)n;  // == epoch  <=> already in the next near list
+  int* mfar = mnear + n;                                         // == fepoch <=> already in the far pile
+  int epoch = 0, fepoch = 0;
+  // marks are never cleared: epochs only grow, across sources too
+  for (int i = tid; i < 2 * n; i += SSSP_THREADS) mnear[i] = 0;
 
   for (int s = blockIdx.x; s < n_sources; s += gridDim.x) {
     double* dist = D + (size_t)s * (size_t)n;
     const int src = (int)sources[s];
     for (int i = tid; i < n; i += SSSP_THREADS) dist[i] = INFINITY;
-    for (int i = tid; i < nwords; i += SSSP_THREADS) { bnear[i] = 0u; bfar[i] = 0u; }
     __syncthreads();
+    ++fepoch;
+    int p = 0;
     if (tid == 0) {
       dist[src] = 0.0;
-      qa[0] = src;
-      s_cnt_near = 1; s_cnt_next = 0; s_cnt_far = 0;
+      qbuf[0][0] = src;
+      s_cnt[0] = 1; s_cnt[1] = 0; s_cnt_far = 0;
       s_thr = delta;
     }
-    __threadfence_block();
     __syncthreads();
     long long rounds = 0, relax = 0, advances = 0;
 
     for (;;) {
       // ---------------- near rounds ----------------
-      int cnt = s_cnt_near;
-      while (cnt > 0) {
-        // (1) entries of qa leave the "queued" state: clear their bits
-        for (int i = tid; i < cnt; i += SSSP_THREADS) {
-          const int u = qa[i];
-          atomicAnd(&bnear[u >> 5], ~(1u << (u & 31)));
-        }
-        __syncthreads();
+      for (;;) {
+        const int cnt = s_cnt[p];
+        if (cnt == 0) break;
+        ++epoch;
+        ++rounds;
         const double thr = s_thr;
-        // (2) relax the arcs of every queued vertex, one warp per vertex
-        for (int i = warp; i < cnt; i += NW) {
-          const int u = qa[i];
-          const double du = ld_cg_f64(dist + u);
-          const int beg = indptr[u], end = indptr[u + 1];
-          for (int e = beg + lane; e < end; e += 32) {
+        const int* qa = qbuf[p];
+        int* qb = qbuf[p ^ 1];
+        for (int c0 = 0; c0 < cnt; c0 += SSSP_THREADS) {
+          // (1) one thread per frontier vertex: tentative distance and row extent
+          const int i = c0 + tid;
+          int deg = 0;
+          if (i < cnt) {
+            const int u = qa[i];
+            const int b = indptr[u];
+            deg = indptr[u + 1] - b;
+            c_du[tid] = __ldcg(dist + u);
+            c_beg[tid] = b;
+          }
+          // (2) block-wide exclusive scan of the degrees
+          int incl = deg;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          if (lane == 31) s_wtot[warp] = incl;
+          __syncthreads();
+          int woff = 0;
+#pragma unroll
+          for (int w = 0; w < SSSP_WARPS; ++w) woff += (w < warp) ? s_wtot[w] : 0;
+          c_pre[tid] = woff + incl - deg;
+          int total = 0;
+#pragma unroll
+          for (int w = 0; w < SSSP_WARPS; ++w) total += s_wtot[w];
+          if (tid == 0) c_pre[SSSP_THREADS] = total;
+          __syncthreads();
+          const int nv = cnt - c0 < SSSP_THREADS ? cnt - c0 : SSSP_THREADS;
+          // (3) one thread per arc: binary search of the owning vertex, relax
+          for (int a = tid; a < total; a += SSSP_THREADS) {
+            int lo = 0, hi = nv - 1;
+            while (lo < hi) {
+              const int mid = (lo + hi + 1) >> 1;
+              if (c_pre[mid] <= a) lo = mid; else hi = mid - 1;
+            }
+            const int e = c_beg[lo] + (a - c_pre[lo]);
             const int v = indices[e];
-            const double nd = du + wts[e];
-            if (nd < ld_cg_f64(dist + v)) {
+            const double nd = c_du[lo] + wts[e];
+            if (nd < __ldcg(dist + v)) {
               const double old = atomic_min_pos_f64(dist + v, nd);
               if (nd < old) {
-                const unsigned int bit = 1u << (v & 31);
                 if (nd < thr) {
-                  if (!(atomicOr(&bnear[v >> 5], bit) & bit)) qb[atomicAdd(&s_cnt_next, 1)] = v;
+                  if (atomicExch(&mnear[v], epoch) != epoch) qb[atomicAdd(&s_cnt[p ^ 1], 1)] = v;
                 } else {
-                  if (!(atomicOr(&bfar[v >> 5], bit) & bit)) far[atomicAdd(&s_cnt_far, 1)] = v;
+                  if (atomicExch(&mfar[v], fepoch) != fepoch) far[atomicAdd(&s_cnt_far, 1)] = v;
                 }
               }
             }
           }
-          if (lane == 0) relax += end - beg;
+          relax += total;  // same value in every thread
+          __syncthreads();
         }
-        __syncthreads();
-        cnt = s_cnt_next;
-        __syncthreads();
-        if (tid == 0) s_cnt_next = 0;
-        int* t = qa; qa = qb; qb = t;
-        ++rounds;
+        if (tid == 0) s_cnt[p] = 0;  // this buffer is the push target of the round after next
+        p ^= 1;
         __syncthreads();
       }
       // ---------------- advance the threshold ----------------
@@ -113,66 +142,61 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_kernel(
       if (nfar == 0) break;
       ++advances;
       double mn = INFINITY;
-      for (int i = tid; i < nfar; i += SSSP_THREADS) mn = fmin(mn, ld_cg_f64(dist + far[i]));
+      for (int i = tid; i < nfar; i += SSSP_THREADS) mn = fmin(mn, __ldcg(dist + far[i]));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
       if (lane == 0) s_red[warp] = mn;
       __syncthreads();
       if (tid == 0) {
         double m2 = INFINITY;
-        for (int q = 0; q < NW; ++q) m2 = fmin(m2, s_red[q]);
+        for (int w = 0; w < SSSP_WARPS; ++w) m2 = fmin(m2, s_red[w]);
         s_thr = m2 + delta;
         s_base_keep = 0;
         s_base_near = 0;
       }
       __syncthreads();
       const double thr2 = s_thr;
-      // split the far pile: entries below the new threshold move to the near list, the
-      // rest are compacted in place (chunks processed in order, so writes trail reads)
+      const int old_fepoch = fepoch;
+      ++fepoch;  // entries that stay in the pile are re-stamped below
+      int* qa = qbuf[p];
+      // split the far pile: entries below the new threshold move to the near list, the rest are
+      // compacted in place (chunks processed in order, so writes trail reads)
       for (int c0 = 0; c0 < nfar; c0 += SSSP_THREADS) {
         const int i = c0 + tid;
         int v = -1;
         bool to_near = false, keep = false;
         if (i < nfar) {
           v = far[i];
-          to_near = ld_cg_f64(dist + v) < thr2;
+          to_near = __ldcg(dist + v) < thr2;
           keep = !to_near;
         }
         const unsigned mk = __ballot_sync(0xffffffffu, keep);
         const unsigned mnr = __ballot_sync(0xffffffffu, to_near);
-        if (lane == 0) { s_scan[warp] = __popc(mk); s_red[warp] = (double)__popc(mnr); }
+        if (lane == 0) { s_wtot[warp] = __popc(mk); s_wtot2[warp] = __popc(mnr); }
         __syncthreads();
         int offk = 0, offn = 0;
-        for (int q = 0; q < warp; ++q) { offk += s_scan[q]; offn += (int)s_red[q]; }
+        for (int w = 0; w < warp; ++w) { offk += s_wtot[w]; offn += s_wtot2[w]; }
         const int bk = s_base_keep, bn = s_base_near;
         __syncthreads();  // every thread has read far[i] and the bases
-        if (keep) far[bk + offk + __popc(mk & ((1u << lane) - 1u))] = v;
-        if (to_near) {
-          qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = v;
-          atomicAnd(&bfar[v >> 5], ~(1u << (v & 31)));
+        if (keep) {
+          far[bk + offk + __popc(mk & ((1u << lane) - 1u))] = v;
+          mfar[v] = fepoch;
         }
+        if (to_near) qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = v;
         if (tid == SSSP_THREADS - 1) {
           s_base_keep = bk + offk + __popc(mk);
           s_base_near = bn + offn + __popc(mnr);
         }
         __syncthreads();
       }
-      if (tid == 0) { s_cnt_far = s_base_keep; s_cnt_near = s_base_near; }
+      (void)old_fepoch;
+      if (tid == 0) { s_cnt_far = s_base_keep; s_cnt[p] = s_base_near; }
       __syncthreads();
     }
-    if (stats) {
-      // relax is accumulated per warp leader; reduce over the block
-      double r = (double)relax;
-      r = warp_sum(r);
-      if (lane == 0) s_red[warp] = r;
-      __syncthreads();
-      if (tid == 0) {
-        double tot = 0;
-        for (int q = 0; q < NW; ++q) tot += s_red[q];
-        stats[(size_t)s * 3 + 0] = rounds;
-        stats[(size_t)s * 3 + 1] = (long long)tot;
-        stats[(size_t)s * 3 + 2] = advances;
-      }
+    if (stats && tid == 0) {
+      stats[(size_t)s * 3 + 0] = rounds;
+      stats[(size_t)s * 3 + 1] = relax;
+      stats[(size_t)s * 3 + 2] = advances;
     }
     __syncthreads();
   }
@@ -192,18 +216,17 @@ int pb200_sssp_num_ctas(int n_sources) {
 
 // D[n_sources][n] = shortest-path distances from sources[s] over the symmetric CSR graph
 // (indptr/indices/wts; every undirected edge stored in both directions).  Unreachable = +inf.
-// scratch: q[n_ctas * 3 * n] int, bits[n_ctas * 2 * ceil(n/32)] uint32 with
+// scratch: q[n_ctas * 3 * n] int, marks[n_ctas * 2 * n] int with
 // n_ctas = pb200_sssp_num_ctas(n_sources); stats (optional) [n_sources][3] int64 =
 // rounds, arcs relaxed, threshold advances.
 int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
-                     int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,
-                     void* stream) {
+                     int n_sources, double delta, double* D, int* q, int* marks, long long* stats, void* stream) {
   if (n_sources <= 0) return 0;
-  if (n >= 2147483647LL) { set_error_msg("pb200_sssp_multi: n too large"); return -1; }
+  if (n >= 1073741823LL) { set_error_msg("pb200_sssp_multi: n too large"); return -1; }
   if (!(delta > 0.0)) { set_error_msg("pb200_sssp_multi: delta must be > 0"); return -1; }
   const int grid = pb200_sssp_num_ctas(n_sources);
   sssp_kernel<<<grid, SSSP_THREADS, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources, n_sources,
-                                                             delta, D, q, bits, stats);
+                                                             delta, D, q, marks, stats);
   PB_CHECK_LAUNCH("sssp_kernel");
   return 0;
 }

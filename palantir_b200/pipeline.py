@@ -28,10 +28,8 @@ def run_device(x_dev: torch.Tensor, early_pos: int, terminal_pos: Optional[Seque
     sink = io.StringIO()
     with (contextlib.redirect_stdout(sink) if quiet else contextlib.nullcontext()):
         # ---- run_diffusion_maps ----
-        q0, nq = _dist.row_shard(n, 256)
         with dv.stage("knn_total"):
-            idx, dist, kstats = dv.knn_like_sklearn(x_dev, min(knn + 1, n), q0, nq)
-            idx, dist = _dist.allgather_rows(idx, dist, n, 256)
+            idx, dist, kstats = dv.knn_like_sklearn(x_dev, min(knn + 1, n), shard=True)
         kern = dv.adaptive_kernel(idx, dist, knn, alpha)
         tvals, lam, U = utils._diffusion_maps_device(kern, n_components, dm_seed)
         # ---- determine_multiscale_space (eigen-gap rule on 10 numbers, column scaling) ----

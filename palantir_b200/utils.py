@@ -30,16 +30,11 @@ LAST_INFO: dict = {}
 def _knn_table(values: np.ndarray, n_neighbors: int):
     """Full neighbour table on the device, query rows sharded across ranks when a
     process group is up (one process per GPU; allgather of the row shards)."""
-    from . import _dist
-
     if values.dtype not in (np.float32, np.float64):
         values = values.astype(np.float64)
     x = dv.to_device(values)
-    n = x.shape[0]
-    q0, nq = _dist.row_shard(n, 256)
     with dv.stage("knn_total"):
-        idx, dist, stats = dv.knn_like_sklearn(x, n_neighbors, q0, nq)
-        idx, dist = _dist.allgather_rows(idx, dist, n, 256)
+        idx, dist, stats = dv.knn_like_sklearn(x, n_neighbors, shard=True)
     LAST_INFO["knn"] = stats
     return idx, dist
 

@@ -9,10 +9,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=151552)
 ap.add_argument("--d", type=int, default=100)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--no-prune", action="store_true")
 a = ap.parse_args()
 x, _ = synth_branching(a.n, a.d)
 xd = dv.to_device(x)
-prep = dv.knn_prepare(xd)
+prep = dv.knn_prepare(xd, prune=not a.no_prune)
 for r in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
