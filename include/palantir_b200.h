@@ -166,9 +166,11 @@ int pb200_point_dists_expanded(const double* data, long long n, int m, long long
 
 /* ---- multi-source shortest paths: scipy.sparse.csgraph.dijkstra(directed=False), core.py:362 ---- */
 int pb200_sssp_num_ctas(int n_sources);
-/* D[n_sources][n]; scratch: q[n_ctas*3*n] int, marks[n_ctas*2*n] int; stats [n_sources][3] or NULL */
+int pb200_sssp_set_ctas_per_sm(int c);
+/* D[n_sources][n]; scratch: q[n_ctas*3*n] int, bits[n_ctas*3*ceil(n/32)] uint32; stats [n_sources][3] or NULL */
 int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
-                     int n_sources, double delta, double* D, int* q, int* marks, long long* stats, void* stream);
+                     int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,
+                     void* stream);
 
 /* ---- pseudotime refinement and projection (core.py:368-397, 225-230) ---- */
 int pb200_sum_pow_f64(const double* x, long long count, double shift, int power, double* partial, double* out,

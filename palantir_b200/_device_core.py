@@ -146,7 +146,7 @@ def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, 
     lib = _native.load()
     n_ctas = lib.pb200_sssp_num_ctas(S)
     q = empty((n_ctas * 3 * n,), I32)
-    marks = empty((n_ctas * 2 * n,), I32)
+    marks = empty((n_ctas * 3 * ((n + 31) // 32),), U32)
     stats = zeros((S, 3), I64) if want_stats else None
     with stage("sssp"):
         call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, marks, stats)

@@ -7,8 +7,9 @@
 // One CTA per source (persistent CTAs loop over the sources), near/far
 // delta-stepping: distances live in the output row D[s][:] (FP64, atomicMin on the
 // bit pattern), the "near" work lists and the "far" pile are per-CTA global buffers
-// that stay L2-resident, epoch-stamped marks de-duplicate pushes without any
-// clearing pass, and only __syncthreads separates rounds -- no grid-wide
+// that stay L2-resident, compact membership bitmaps (N/8 bytes each, so the working
+// set of all resident sources fits L2) de-duplicate pushes, and only
+// __syncthreads separates rounds -- no grid-wide
 // synchronisation, no host round trips.  The graph Palantir runs this on is long and
 // thin (shortest-path trees tens of thousands of hops deep at 1 M cells, SURVEY.md
 // 7b-2), so a source needs ~3*10^4 rounds of a few dozen vertices each: the kernel is
@@ -30,7 +31,7 @@ constexpr int SSSP_WARPS = SSSP_THREADS / 32;
 __global__ void __launch_bounds__(SSSP_THREADS) sssp_kernel(
     const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ wts, int n,
     const long long* __restrict__ sources, int n_sources, double delta, double* __restrict__ D,
-    int* __restrict__ q_all, int* __restrict__ marks_all, long long* __restrict__ stats) {
+    int* __restrict__ q_all, unsigned int* __restrict__ bits_all, long long* __restrict__ stats) {
   __shared__ int s_cnt[2];
   __shared__ int s_cnt_far;
   __shared__ double s_thr;
@@ -47,18 +48,20 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_kernel(
   qbuf[0] = q_all + (size_t)blockIdx.x * 3 * (size_t)n;
   qbuf[1] = qbuf[0] + n;
   int* far = qbuf[1] + n;
-  int* mnear = marks_all + (size_t)blockIdx.x * 2 * (size_t)n;  // == epoch  <=> already in the next near list
-  int* mfar = mnear + n;                                         // == fepoch <=> already in the far pile
-  int epoch = 0, fepoch = 0;
-  // marks are never cleared: epochs only grow, across sources too
-  for (int i = tid; i < 2 * n; i += SSSP_THREADS) mnear[i] = 0;
+  const int nwords = (n + 31) >> 5;
+  // bnear[p]: members of near list p; a vertex clears its bit when it is popped, so the list that
+  // is being filled never needs a separate clearing pass.  bfar: members of the far pile.
+  unsigned int* bnear[2];
+  bnear[0] = bits_all + (size_t)blockIdx.x * 3 * (size_t)nwords;
+  bnear[1] = bnear[0] + nwords;
+  unsigned int* bfar = bnear[1] + nwords;
 
   for (int s = blockIdx.x; s < n_sources; s += gridDim.x) {
     double* dist = D + (size_t)s * (size_t)n;
     const int src = (int)sources[s];
     for (int i = tid; i < n; i += SSSP_THREADS) dist[i] = INFINITY;
+    for (int i = tid; i < 3 * nwords; i += SSSP_THREADS) bnear[0][i] = 0u;
     __syncthreads();
-    ++fepoch;
     int p = 0;
     if (tid == 0) {
       dist[src] = 0.0;
@@ -74,17 +77,19 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_kernel(
       for (;;) {
         const int cnt = s_cnt[p];
         if (cnt == 0) break;
-        ++epoch;
         ++rounds;
         const double thr = s_thr;
         const int* qa = qbuf[p];
         int* qb = qbuf[p ^ 1];
+        unsigned int* bcur = bnear[p];
+        unsigned int* bnext = bnear[p ^ 1];
         for (int c0 = 0; c0 < cnt; c0 += SSSP_THREADS) {
           // (1) one thread per frontier vertex: tentative distance and row extent
           const int i = c0 + tid;
           int deg = 0;
           if (i < cnt) {
             const int u = qa[i];
+            atomicAnd(&bcur[u >> 5], ~(1u << (u & 31)));   // popped
             const int b = indptr[u];
             deg = indptr[u + 1] - b;
             c_du[tid] = __ldcg(dist + u);
@@ -122,10 +127,11 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_kernel(
             if (nd < __ldcg(dist + v)) {
               const double old = atomic_min_pos_f64(dist + v, nd);
               if (nd < old) {
+                const unsigned int bit = 1u << (v & 31);
                 if (nd < thr) {
-                  if (atomicExch(&mnear[v], epoch) != epoch) qb[atomicAdd(&s_cnt[p ^ 1], 1)] = v;
+                  if (!(atomicOr(&bnext[v >> 5], bit) & bit)) qb[atomicAdd(&s_cnt[p ^ 1], 1)] = v;
                 } else {
-                  if (atomicExch(&mfar[v], fepoch) != fepoch) far[atomicAdd(&s_cnt_far, 1)] = v;
+                  if (!(atomicOr(&bfar[v >> 5], bit) & bit)) far[atomicAdd(&s_cnt_far, 1)] = v;
                 }
               }
             }
@@ -156,9 +162,8 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_kernel(
       }
       __syncthreads();
       const double thr2 = s_thr;
-      const int old_fepoch = fepoch;
-      ++fepoch;  // entries that stay in the pile are re-stamped below
       int* qa = qbuf[p];
+      unsigned int* bcur = bnear[p];
       // split the far pile: entries below the new threshold move to the near list, the rest are
       // compacted in place (chunks processed in order, so writes trail reads)
       for (int c0 = 0; c0 < nfar; c0 += SSSP_THREADS) {
@@ -178,18 +183,18 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_kernel(
         for (int w = 0; w < warp; ++w) { offk += s_wtot[w]; offn += s_wtot2[w]; }
         const int bk = s_base_keep, bn = s_base_near;
         __syncthreads();  // every thread has read far[i] and the bases
-        if (keep) {
-          far[bk + offk + __popc(mk & ((1u << lane) - 1u))] = v;
-          mfar[v] = fepoch;
+        if (keep) far[bk + offk + __popc(mk & ((1u << lane) - 1u))] = v;
+        if (to_near) {
+          qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = v;
+          atomicAnd(&bfar[v >> 5], ~(1u << (v & 31)));
+          atomicOr(&bcur[v >> 5], 1u << (v & 31));
         }
-        if (to_near) qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = v;
         if (tid == SSSP_THREADS - 1) {
           s_base_keep = bk + offk + __popc(mk);
           s_base_near = bn + offn + __popc(mnr);
         }
         __syncthreads();
       }
-      (void)old_fepoch;
       if (tid == 0) { s_cnt_far = s_base_keep; s_cnt[p] = s_base_near; }
       __syncthreads();
     }
@@ -208,25 +213,35 @@ using namespace pb200;
 
 extern "C" {
 
+static int g_sssp_ctas_per_sm = 4;
+
+// Tuning knob: resident CTAs (= concurrently processed sources) per SM, 1..4.
+int pb200_sssp_set_ctas_per_sm(int c) {
+  if (c < 1 || c > 4) { set_error_msg("pb200_sssp_set_ctas_per_sm: 1..4"); return -1; }
+  g_sssp_ctas_per_sm = c;
+  return 0;
+}
+
 // Number of resident CTAs the launch will use (scratch is sized per CTA).
 int pb200_sssp_num_ctas(int n_sources) {
-  const int cap = 4 * kSMs;
+  const int cap = g_sssp_ctas_per_sm * kSMs;
   return n_sources < cap ? n_sources : cap;
 }
 
 // D[n_sources][n] = shortest-path distances from sources[s] over the symmetric CSR graph
 // (indptr/indices/wts; every undirected edge stored in both directions).  Unreachable = +inf.
-// scratch: q[n_ctas * 3 * n] int, marks[n_ctas * 2 * n] int with
+// scratch: q[n_ctas * 3 * n] int, bits[n_ctas * 3 * ceil(n/32)] uint32 with
 // n_ctas = pb200_sssp_num_ctas(n_sources); stats (optional) [n_sources][3] int64 =
 // rounds, arcs relaxed, threshold advances.
 int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
-                     int n_sources, double delta, double* D, int* q, int* marks, long long* stats, void* stream) {
+                     int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,
+                     void* stream) {
   if (n_sources <= 0) return 0;
   if (n >= 1073741823LL) { set_error_msg("pb200_sssp_multi: n too large"); return -1; }
   if (!(delta > 0.0)) { set_error_msg("pb200_sssp_multi: delta must be > 0"); return -1; }
   const int grid = pb200_sssp_num_ctas(n_sources);
   sssp_kernel<<<grid, SSSP_THREADS, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources, n_sources,
-                                                             delta, D, q, marks, stats);
+                                                             delta, D, q, bits, stats);
   PB_CHECK_LAUNCH("sssp_kernel");
   return 0;
 }

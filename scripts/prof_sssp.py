@@ -1,0 +1,27 @@
+"""SSSP timing on the benchmark graph with tuning knobs (dev tool)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from palantir_b200 import _device as dv, _device_core as dc, _native
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+rng = np.random.default_rng(0)
+# a thick noisy curve in 6-D, like the min-max scaled multiscale space
+t = np.sort(rng.random(n))
+data = np.stack([t, np.sin(3 * t) * 0.5 + 0.5, np.cos(5 * t) * 0.5 + 0.5, t ** 2, np.sqrt(t), 0.5 + 0.3 * np.sin(9 * t)], 1)
+data += rng.normal(size=data.shape) * 2e-3
+dev = dv.to_device(np.ascontiguousarray(data))
+perm, inv, work = dc.locality_order(dev)
+idx, dist, st = dc.knn_table_sorted(work, 30)
+g = dc.undirected_graph(idx, dist)
+src = dv.to_device(rng.choice(n, 1198, replace=False).astype(np.int64))
+lib = _native.load()
+mean_w = float(g.data.mean().item())
+print("arcs", g.nnz, "mean w", mean_w)
+for ctas in (4, 2, 1):
+    lib.pb200_sssp_set_ctas_per_sm(ctas)
+    for mult in (2.0, 4.0, 8.0, 16.0):
+        torch.cuda.synchronize(); t0 = time.time()
+        D, stats = dc.sssp(g, src, delta=mult * mean_w, want_stats=True)
+        torch.cuda.synchronize(); dt = time.time() - t0
+        s = stats.double().mean(0).cpu().numpy()
+        print(f"ctas/SM {ctas} delta {mult}x: {dt*1e3:.1f} ms rounds {s[0]:.0f} relax/arcs {s[1]/g.nnz:.2f} advances {s[2]:.0f}", flush=True)
