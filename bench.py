@@ -203,6 +203,7 @@ def run_gpu_arm(args):
     e1.record()
     barrier()
     launches = _native.launch_count() - l0
+    sssp_info = dict(core.LAST_INFO.get("sssp", {}))
     dv.flush_profile()
     prof = {k: v / args.steps for k, v in dv.PROFILE.items()}
     dv.PROFILE = None
@@ -281,7 +282,6 @@ def run_gpu_arm(args):
     spmv_ms = s0.elapsed_time(s1) / reps
     spmv_bytes = kd.nnz * 12 + (n + 1) * 4 + n * 8 + n * 8
     spmv_gbs = spmv_bytes / spmv_ms / 1e6
-    sssp_info = core.LAST_INFO.get("sssp", {})
     sssp_ms = prof.get("sssp")
     arcs_s = (sssp_info.get("sources", 0) * sssp_info.get("arcs", 0) / (sssp_ms / 1e3)) if sssp_ms else None
 

@@ -51,18 +51,19 @@ int pb200_weighted_col_sums(const void* x, int is_f64, long long n, int d, const
 int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, long long ld, const double* mean,
                       const int* perm, float* xt, float* yn, double* xcn, double* xn64, double* rmax2,
                       void* stream);
-/* lo[t] / hi[t] = projection of the first / last point of work-order tile t (proj indexed by input row). */
-int pb200_tile_intervals(const double* proj, const int* perm, long long n, long long ntiles, double* lo, double* hi,
-                         void* stream);
+/* box_lo / box_hi [ntiles][3]: bounding box of the three projections proj[3][n] (structure of arrays,
+ * indexed by input row) of every 128-point work-order tile; padding tiles get (+inf, -inf). */
+int pb200_tile_boxes(const double* proj, const int* perm, long long n, long long ntiles, double* box_lo,
+                     double* box_hi, void* stream);
 
 /* FP32 candidate generation: for work-order points q0..q0+nq-1 (q0 % 256 == 0) keep the k_keep (<= 48)
- * smallest scores |y|^2 - 2 x.y over all n_pad points.  With tile_lo / tile_hi (projection intervals of the
- * 128-point tiles of points sorted along a unit direction; NULL = none) reference tiles that provably cannot
+ * smallest scores |y|^2 - 2 x.y over all n_pad points.  With box_lo / box_hi (pb200_tile_boxes: boxes of the
+ * projections on three orthonormal directions; NULL = none) reference tiles that provably cannot
  * contribute are skipped.  out_idx/out_score [nq][k_keep] ascending (work-order indices), out_thr[nq] =
  * k_keep-th score (lower bound for every excluded reference; +inf if nothing excluded).
  * scratch: lists[ceil(nq/256)*256*64] 64-bit words; tiles_visited: optional counter. */
 int pb200_knn_candidates_f32(const float* xt, long long n_pad, const float* yn, const double* xcn,
-                             const double* tile_lo, const double* tile_hi, int q0, int nq, int d, int d_pad,
+                             const double* box_lo, const double* box_hi, int q0, int nq, int d, int d_pad,
                              int k_keep, unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
                              unsigned long long* tiles_visited, void* stream);
 
@@ -101,6 +102,9 @@ int pb200_knn_sorted_f64(const double* data, long long n, int m, int q0, int nq,
 long long pb200_argsort_scratch_bytes(long long n);
 int pb200_argsort_col_f64(const double* data, long long n, int m, int col, int* perm, int* inv, void* scratch,
                           long long scratch_bytes, void* stream);
+/* Morton order of n points from three projections proj[3][n]: 21 bits per axis, origin lo*, cell 1/inv_cell */
+int pb200_morton_order(const double* proj, long long n, double lo0, double lo1, double lo2, double inv_cell,
+                       int* perm, int* inv, void* scratch, long long scratch_bytes, void* stream);
 /* out[i] = a[perm[i]]  /  out[perm[i]] = a[i]   (rows of m doubles) */
 int pb200_permute_rows_f64(const double* a, long long n, int m, const int* perm, double* out, void* stream);
 int pb200_unpermute_rows_f64(const double* a, long long n, int m, const int* perm, double* out, void* stream);
@@ -167,6 +171,7 @@ int pb200_point_dists_expanded(const double* data, long long n, int m, long long
 /* ---- multi-source shortest paths: scipy.sparse.csgraph.dijkstra(directed=False), core.py:362 ---- */
 int pb200_sssp_num_ctas(int n_sources);
 int pb200_sssp_set_ctas_per_sm(int c);
+int pb200_sssp_set_variant(int v);
 /* D[n_sources][n]; scratch: q[n_ctas*3*n] int, bits[n_ctas*3*ceil(n/32)] uint32; stats [n_sources][3] or NULL */
 int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
                      int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,

@@ -99,41 +99,48 @@ class KnnPrep:
     xcn: torch.Tensor
     xn64: torch.Tensor
     rmax2: torch.Tensor
-    tile_lo: Optional[torch.Tensor]
-    tile_hi: Optional[torch.Tensor]
+    box_lo: Optional[torch.Tensor]    # [ntiles, 3] projection boxes of the 128-point tiles
+    box_hi: Optional[torch.Tensor]
     n: int
     d: int
     d_pad: int
     ld: int
 
 
-def principal_direction(x: torch.Tensor, mean: torch.Tensor, iters: int = 12) -> torch.Tensor:
-    """Leading principal axis of the centred data by power iteration on X^T X (two passes over X
-    per step).  Only the *quality* of the pruning depends on it: any unit vector gives a valid bound."""
+def principal_axes(x: torch.Tensor, mean: torch.Tensor, n_axes: int = 3, iters: int = 10) -> torch.Tensor:
+    """Leading principal axes of the centred data ([n_axes, d], orthonormal, norm scaled just below 1)
+    by power iteration on X^T X with deflation (two passes over X per step, no host sync).  Only the
+    *quality* of the pruning depends on them: any orthonormal set gives valid bounds."""
     from . import _dist
 
     n, d = x.shape
     is64 = int(x.dtype == F64)
-    v = torch.full((d,), 1.0 / math.sqrt(d), dtype=F64, device=x.device)
+    n_axes = min(n_axes, d)
     proj = empty((n,), F64)
     w = empty((d,), F64)
-    for _ in range(iters):
-        call("pb200_project_rows", x, is64, n, d, mean, v, proj)
-        call("pb200_weighted_col_sums", x, is64, n, d, mean, proj, w)
-        nrm = float(torch.linalg.vector_norm(w).item())
-        if not (nrm > 0.0):
-            break
-        v = w / nrm
-    v = (v / torch.linalg.vector_norm(v)) * (1.0 - 1e-12)       # |v| <= 1: projections never exceed distances
-    _dist.broadcast_(v)                                         # every rank must sort identically
-    return v.contiguous()
+    idx = torch.arange(d, dtype=F64, device=x.device)
+    axes = []
+    for a in range(n_axes):
+        v = torch.cos((idx + 1.0) * (a + 1.0) * 0.7390851)          # deterministic, generic start
+        for it in range(iters + 1):
+            for u in axes:
+                v = v - torch.dot(v, u) * u
+            v = (v / torch.linalg.vector_norm(v)).contiguous()
+            if it == iters:
+                break
+            call("pb200_project_rows", x, is64, n, d, mean, v, proj)
+            call("pb200_weighted_col_sums", x, is64, n, d, mean, proj, w)
+            v = w.clone()
+        axes.append(v)
+    V = (torch.stack(axes) * (1.0 - 1e-12)).contiguous()             # |v| <= 1: projections never exceed distances
+    _dist.broadcast_(V)                                              # every rank must order identically
+    return V
 
 
 def knn_prepare(x: torch.Tensor, prune: bool = True) -> KnnPrep:
-    """Mean-centre, sort the points along the leading principal axis (work order) and build the
-    candidate kernel's operands."""
-    from . import _device_core as dc_                      # argsort helper lives with the palantir stages
-
+    """Mean-centre, order the points along the Morton curve of their projections on the three
+    leading principal axes (work order), box every 128-point tile and build the candidate kernel's
+    operands."""
     n, d = x.shape
     if x.dtype not in (F32, F64):
         raise TypeError("kNN input must be float32 or float64")
@@ -142,22 +149,33 @@ def knn_prepare(x: torch.Tensor, prune: bool = True) -> KnnPrep:
     is64 = int(x.dtype == F64)
     mean = empty((d,), F64)
     call("pb200_col_means", x, is64, n, d, mean)
-    perm = tile_lo = tile_hi = None
-    if prune and n > 512:
-        v = principal_direction(x, mean)
-        proj = empty((n,), F64)
-        call("pb200_project_rows", x, is64, n, d, mean, v, proj)
-        perm, _inv, _ = dc_.locality_order(proj.view(n, 1), want_sorted=False)
+    perm = box_lo = box_hi = None
+    if prune and n > 512 and d >= 3:
+        V = principal_axes(x, mean)
+        proj = empty((3, n), F64)
+        for a in range(3):
+            call("pb200_project_rows", x, is64, n, d, mean, V[a].contiguous(), proj[a])
+        lo = proj.amin(dim=1).cpu()
+        hi = proj.amax(dim=1).cpu()
+        ext = float((hi - lo).max().item())
+        inv_cell = (2 ** 21 - 1) / ext if ext > 0.0 else 1.0
+        lib = _native.load()
+        nbytes = int(lib.pb200_argsort_scratch_bytes(n))
+        scratch = empty((nbytes,), torch.uint8)
+        perm, inv = empty((n,), I32), empty((n,), I32)
+        call("pb200_morton_order", proj, n, float(lo[0]), float(lo[1]), float(lo[2]), float(inv_cell), perm, inv,
+             scratch, nbytes)
         ntiles = ld // 128
-        tile_lo, tile_hi = empty((ntiles,), F64), empty((ntiles,), F64)
-        call("pb200_tile_intervals", proj, perm, n, ntiles, tile_lo, tile_hi)
+        box_lo, box_hi = empty((ntiles, 3), F64), empty((ntiles, 3), F64)
+        call("pb200_tile_boxes", proj, perm, n, ntiles, box_lo, box_hi)
+        del scratch, inv
     xt = empty((d_pad * ld,), F32)
     yn = empty((ld,), F32)
     xcn = empty((n,), F64)
     xn64 = empty((n,), F64)
     rmax2 = empty((1,), F64)
     call("pb200_knn_prepare", x, is64, n, d, d_pad, ld, mean, perm, xt, yn, xcn, xn64, rmax2)
-    return KnnPrep(x, perm, xt, yn, xcn, xn64, rmax2, tile_lo, tile_hi, n, d, d_pad, ld)
+    return KnnPrep(x, perm, xt, yn, xcn, xn64, rmax2, box_lo, box_hi, n, d, d_pad, ld)
 
 
 def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
@@ -189,7 +207,7 @@ def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
     lists = empty((round_up(nq, 256) * 64,), I64)
     visited = zeros((1,), I64)
     with stage("knn_candidates"):
-        call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.yn, prep.xcn, prep.tile_lo, prep.tile_hi, q0, nq,
+        call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.yn, prep.xcn, prep.box_lo, prep.box_hi, q0, nq,
              prep.d, prep.d_pad, k_keep, lists, cand, score, thr, visited)
     del lists
     flag = empty((nq,), U8)

@@ -11,16 +11,17 @@
 // k, and proves with an FP32 error bound that no excluded point can belong to the
 // true top-k (rows that cannot be proven are redone exactly in FP64).
 //
-// Work order and exact pruning.  The points are sorted along a unit direction v
-// (the leading principal axis, see _device.knn_prepare) and processed in that
-// order.  Since |v.(x - y)| <= |x - y|, a 128-point reference tile whose projection
-// interval lies further than g from the projection interval of a CTA's 256 query
-// rows can only contain points at distance >= g.  A CTA therefore walks the
-// reference tiles outwards from its own position (right, left, right, ...) and
-// drops a side for good once g^2 exceeds max_rows(thr_row + |x_row|^2), the largest
-// squared distance any of its rows could still accept.  Every dropped reference has
-// a true score above the row's threshold, which is what the re-rank certificate
-// needs.
+// Work order and exact pruning.  The points are projected on three orthonormal
+// directions (the leading principal axes, see _device.knn_prepare), ordered along
+// the Morton curve of those projections, and every 128-point tile carries the
+// bounding box of its projections.  A projection never lengthens a vector, so a
+// reference tile whose box lies at distance g from the box of a CTA's 256 query rows
+// can only contain points at distance >= g.  A CTA visits the tiles outwards from
+// its own position (right, left, right, ... -- near tiles first, so thresholds
+// tighten early) and skips every tile with g^2 > max_rows(thr_row + |x_row|^2), the
+// largest squared distance any of its rows could still accept.  Every skipped
+// reference has a true score above the row's threshold, which is what the re-rank
+// certificate needs.
 //
 // Layout: coordinates are stored tiled and k-major ("XT"): point i = 128*tile + il,
 // coordinate c = 16*kc + k lives at XT[((tile*KCH + kc)*16 + k)*128 + il], so the
@@ -30,9 +31,9 @@
 // to a multiple of 256.  A CTA owns 256 query rows and streams reference tiles
 // through an 8-stage shared-memory ring filled by the TMA engine (cp.async.bulk +
 // mbarrier full/empty pairs).  There is no producer warp and nobody blocks on an
-// "empty" barrier: at the top of every chunk each warp's lane 0 try-locks the
-// producer state and, if the next stage has been released, decides the next tile
-// and issues its copies.  16 warps each own 16 query rows x 128 reference columns
+// "empty" barrier: at the top of every chunk a warp try-locks the producer state
+// and, if the next stage has been released, picks the next tile (32 box tests per
+// step, one per lane) and issues its copies.  16 warps each own 16 query rows x 128 reference columns
 // (8x8 register micro-tile per thread), so the top-K lists of a row (L2-resident
 // global scratch; only count and threshold live in shared memory) are only ever
 // touched by one warp and the selection needs no CTA-wide barrier.  One CTA per
@@ -72,16 +73,17 @@ struct KnnSmem {
   int lock;
   int next_chunk;               // number of chunks issued so far
   int cur_tile, cur_kc;
-  int left, right;
-  int l_done, r_done, turn, ended;
+  int cursor;                   // position in the outward visiting sequence
+  int ended;
+  double qlo[3], qhi[3];        // projection box of the CTA's query rows
 };
 
 struct KnnParams {
   const float* xt;        // coordinates, tiled k-major (queries are a row range of the same set)
   const float* yn;        // |y_j|^2 per point (FP32, +inf on padding)
   const double* xcn;      // |x_i|^2 per point (FP64, centred)
-  const double* tile_lo;  // projection interval of every 128-point tile (NULL: no pruning)
-  const double* tile_hi;
+  const double* box_lo;   // [n_tiles][3] projection box of every 128-point tile (NULL: no pruning)
+  const double* box_hi;
   int q0;                 // first query point (multiple of 256)
   int nq;                 // number of query rows handled by this launch
   int n_tiles;            // padded point count / 128
@@ -99,71 +101,101 @@ __device__ __forceinline__ unsigned long long pack_entry(float s, int idx) {
   return ((unsigned long long)f32_ordered(s) << 32) | (unsigned int)idx;
 }
 
-// Producer step, called by one thread holding sm.lock: while the next stage is free, pick the
-// next (tile, kc) chunk -- walking the tiles outwards and pruning sides -- and issue its copies.
-__device__ __noinline__ void knn_produce(KnnSmem* smp, const KnnParams* pp, int qtile0, int max_issue) {
+// s-th tile of the outward visiting sequence of a CTA whose first query tile is q: q, q-1, q+1, q-2, ...
+// until one side runs out, then the rest of the other side.
+__device__ __forceinline__ int knn_tile_of(int s, int q, int T) {
+  const int R = T - q, L = q;
+  const int m = R < L ? R : L;
+  if (s < 2 * m) return (s & 1) ? q - 1 - (s >> 1) : q + (s >> 1);
+  const int rest = s - 2 * m;
+  return R > L ? q + m + rest : q - 1 - m - rest;
+}
+
+// Producer step, executed by one whole warp that holds sm.lock: while the next stage is free, pick
+// the next (tile, kc) chunk -- visiting tiles outwards and skipping those whose projection box is
+// out of reach (32 box tests at a time, one per lane) -- and issue its copies (lane 0).
+__device__ __noinline__ void knn_produce(KnnSmem* smp, const KnnParams* pp, int qtile0, int max_issue, int lane) {
   KnnSmem& sm = *smp;
   const KnnParams& p = *pp;
   const int KCH = p.kch;
+  const int T = p.n_tiles;
   for (int it = 0; it < max_issue; ++it) {
     if (sm.ended) return;
     const int g = sm.next_chunk;
     const int st = g % KNN_NST;
     if (!mbar_test(&sm.empty[st], (((uint32_t)(g / KNN_NST)) & 1u) ^ 1u)) return;
     if (sm.cur_kc == 0) {
-      // choose the next reference tile
       float bmax = sm.warp_bound[0];
 #pragma unroll
       for (int w = 1; w < KNN_WARPS; ++w) bmax = fmaxf(bmax, sm.warp_bound[w]);
       const double bound = (double)bmax;
-      int t = -1;
-      while (t < 0) {
-        if (sm.r_done && sm.l_done) break;
-        const bool go_right = (sm.turn == 0 && !sm.r_done) || sm.l_done;
-        sm.turn ^= 1;
-        if (go_right) {
-          if (sm.right >= p.n_tiles) { sm.r_done = 1; continue; }
-          if (p.tile_lo) {
-            double gap = p.tile_lo[sm.right] - p.tile_hi[qtile0 + 1];
-            gap = gap > 0.0 ? gap : 0.0;
-            if (gap * gap * (1.0 - 1e-9) > bound) { sm.r_done = 1; continue; }
+      int chosen = -1;
+      for (;;) {
+        const int s0 = sm.cursor;
+        if (s0 >= T) break;
+        const int sidx = s0 + lane;
+        const int tile = sidx < T ? knn_tile_of(sidx, qtile0, T) : -1;
+        bool ok = false;
+        if (tile >= 0) {
+          if (!p.box_lo) {
+            ok = true;
+          } else {
+            double g2 = 0.0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              const double d1 = p.box_lo[(long long)tile * 3 + a] - sm.qhi[a];
+              const double d2 = sm.qlo[a] - p.box_hi[(long long)tile * 3 + a];
+              double gp = d1 > d2 ? d1 : d2;
+              gp = gp > 0.0 ? gp : 0.0;
+              g2 = fma(gp, gp, g2);
+            }
+            ok = !(g2 * (1.0 - 1e-9) > bound);       // +inf boxes (padding tiles) are never ok
           }
-          t = sm.right++;
-        } else {
-          if (sm.left < 0) { sm.l_done = 1; continue; }
-          if (p.tile_lo) {
-            double gap = p.tile_lo[qtile0] - p.tile_hi[sm.left];
-            gap = gap > 0.0 ? gap : 0.0;
-            if (gap * gap * (1.0 - 1e-9) > bound) { sm.l_done = 1; continue; }
-          }
-          t = sm.left--;
         }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        __syncwarp();
+        if (m) {
+          const int first = __ffs(m) - 1;
+          chosen = __shfl_sync(0xffffffffu, tile, first);
+          if (lane == 0) sm.cursor = s0 + first + 1;
+          __syncwarp();
+          break;
+        }
+        if (lane == 0) sm.cursor = s0 + 32;
+        __syncwarp();
       }
-      if (t < 0) {
+      if (chosen < 0) {
         // end of stream: a data-less completion of this stage's "full" barrier
-        sm.meta_tile[st] = -1;
-        sm.ended = 1;
-        sm.next_chunk = g + 1;
-        mbar_arrive(&sm.full[st]);
+        if (lane == 0) {
+          sm.meta_tile[st] = -1;
+          sm.ended = 1;
+          sm.next_chunk = g + 1;
+          mbar_arrive(&sm.full[st]);
+        }
+        __syncwarp();
         return;
       }
-      sm.cur_tile = t;
+      if (lane == 0) sm.cur_tile = chosen;
+      __syncwarp();
     }
-    const int t = sm.cur_tile, kc = sm.cur_kc;
-    sm.meta_tile[st] = t;
-    sm.meta_kc[st] = kc;
-    const bool last = (kc == KCH - 1);
-    const uint32_t blk_bytes = (uint32_t)(last ? p.k_tail : KNN_DK) * KNN_BN * 4u;
-    mbar_arrive_expect_tx(&sm.full[st], 3u * blk_bytes + (last ? KNN_BN * 4u : 0u));
-    const float* a0 = p.xt + ((long long)qtile0 * KCH + kc) * KNN_BLOCK_FLOATS;
-    const float* a1 = a0 + (long long)KCH * KNN_BLOCK_FLOATS;
-    const float* br = p.xt + ((long long)t * KCH + kc) * KNN_BLOCK_FLOATS;
-    bulk_g2s(&sm.st[st].a[0][0][0], a0, blk_bytes, &sm.full[st]);
-    bulk_g2s(&sm.st[st].a[1][0][0], a1, blk_bytes, &sm.full[st]);
-    bulk_g2s(&sm.st[st].b[0][0], br, blk_bytes, &sm.full[st]);
-    if (last) bulk_g2s(&sm.st[st].yn[0], p.yn + (long long)t * KNN_BN, KNN_BN * 4, &sm.full[st]);
-    sm.cur_kc = last ? 0 : kc + 1;
-    sm.next_chunk = g + 1;
+    if (lane == 0) {
+      const int t = sm.cur_tile, kc = sm.cur_kc;
+      sm.meta_tile[st] = t;
+      sm.meta_kc[st] = kc;
+      const bool last = (kc == KCH - 1);
+      const uint32_t blk_bytes = (uint32_t)(last ? p.k_tail : KNN_DK) * KNN_BN * 4u;
+      mbar_arrive_expect_tx(&sm.full[st], 3u * blk_bytes + (last ? KNN_BN * 4u : 0u));
+      const float* a0 = p.xt + ((long long)qtile0 * KCH + kc) * KNN_BLOCK_FLOATS;
+      const float* a1 = a0 + (long long)KCH * KNN_BLOCK_FLOATS;
+      const float* br = p.xt + ((long long)t * KCH + kc) * KNN_BLOCK_FLOATS;
+      bulk_g2s(&sm.st[st].a[0][0][0], a0, blk_bytes, &sm.full[st]);
+      bulk_g2s(&sm.st[st].a[1][0][0], a1, blk_bytes, &sm.full[st]);
+      bulk_g2s(&sm.st[st].b[0][0], br, blk_bytes, &sm.full[st]);
+      if (last) bulk_g2s(&sm.st[st].yn[0], p.yn + (long long)t * KNN_BN, KNN_BN * 4, &sm.full[st]);
+      sm.cur_kc = last ? 0 : kc + 1;
+      sm.next_chunk = g + 1;
+    }
+    __syncwarp();
   }
 }
 
@@ -219,12 +251,16 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
     }
     fence_mbar_init();
     sm.lock = 0; sm.next_chunk = 0; sm.cur_tile = 0; sm.cur_kc = 0;
-    sm.right = qtile0;
-    sm.left = qtile0 - 1;
-    sm.l_done = 0; sm.r_done = 0; sm.turn = 0; sm.ended = 0;
+    sm.cursor = 0; sm.ended = 0;
+    if (p.box_lo) {
+      for (int a = 0; a < 3; ++a) {
+        sm.qlo[a] = fmin(p.box_lo[(long long)qtile0 * 3 + a], p.box_lo[(long long)(qtile0 + 1) * 3 + a]);
+        sm.qhi[a] = fmax(p.box_hi[(long long)qtile0 * 3 + a], p.box_hi[(long long)(qtile0 + 1) * 3 + a]);
+      }
+    }
   }
   __syncthreads();
-  if (tid == 0) knn_produce(&sm, &p, qtile0, KNN_NST);
+  if (warp == 0) knn_produce(&sm, &p, qtile0, KNN_NST, lane);
   __syncthreads();
 
   const int KCH = p.kch;
@@ -238,11 +274,17 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
   float ynr[8];
 
   for (;;) {
-    if (lane == 0 && !*(volatile int*)&sm.ended && atomicCAS(&sm.lock, 0, 1) == 0) {
-      __threadfence_block();
-      knn_produce(&sm, &p, qtile0, 2);
-      __threadfence_block();
-      atomicExch(&sm.lock, 0);
+    {
+      int got = 0;
+      if (lane == 0 && !*(volatile int*)&sm.ended) got = (atomicCAS(&sm.lock, 0, 1) == 0);
+      got = __shfl_sync(0xffffffffu, got, 0);
+      if (got) {
+        __threadfence_block();
+        knn_produce(&sm, &p, qtile0, 2, lane);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) atomicExch(&sm.lock, 0);
+      }
     }
     __syncwarp();
     mbar_wait(&sm.full[stage], phase);
@@ -498,19 +540,6 @@ __global__ void knn_prep_kernel(const T* __restrict__ x, long long n, int d, int
   }
 }
 
-// interval [lo, hi] of the (sorted) projections of each 128-point tile
-__global__ void tile_intervals_kernel(const double* __restrict__ proj, const int* __restrict__ perm, long long n,
-                                      long long ntiles, double* __restrict__ lo, double* __restrict__ hi) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntiles) return;
-  const long long a = t * KNN_BN;
-  long long b = a + KNN_BN - 1;
-  if (a >= n) { lo[t] = INFINITY; hi[t] = INFINITY; return; }   // pure padding tile: pruned at once
-  if (b > n - 1) b = n - 1;
-  lo[t] = proj[perm[a]];
-  hi[t] = proj[perm[b]];
-}
-
 __global__ void scale_to_mean_kernel(double* v, int d, double inv_n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < d) v[c] *= inv_n;
@@ -599,16 +628,8 @@ int pb200_knn_prepare(const void* x, int is_f64, long long n, int d, int d_pad, 
   return 0;
 }
 
-// lo[t], hi[t] = projection of the first / last point of work-order tile t (proj indexed by source row)
-int pb200_tile_intervals(const double* proj, const int* perm, long long n, long long ntiles, double* lo, double* hi,
-                         void* stream) {
-  tile_intervals_kernel<<<div_up(ntiles, 256), 256, 0, (cudaStream_t)stream>>>(proj, perm, n, ntiles, lo, hi);
-  PB_CHECK_LAUNCH("tile_intervals_kernel");
-  return 0;
-}
-
 int pb200_knn_candidates_f32(const float* xt, long long n_pad, const float* yn, const double* xcn,
-                             const double* tile_lo, const double* tile_hi, int q0, int nq, int d, int d_pad,
+                             const double* box_lo, const double* box_hi, int q0, int nq, int d, int d_pad,
                              int k_keep, unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
                              unsigned long long* tiles_visited, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -624,7 +645,7 @@ int pb200_knn_candidates_f32(const float* xt, long long n_pad, const float* yn, 
     return -1;
   }
   KnnParams p;
-  p.xt = xt; p.yn = yn; p.xcn = xcn; p.tile_lo = tile_lo; p.tile_hi = tile_hi;
+  p.xt = xt; p.yn = yn; p.xcn = xcn; p.box_lo = box_lo; p.box_hi = box_hi;
   p.q0 = q0; p.nq = nq; p.n_tiles = (int)(n_pad / KNN_BN);
   p.kch = d_pad / KNN_DK; p.k_keep = k_keep;
   p.k_tail = ((d - (d_pad - KNN_DK)) + 3) / 4 * 4;

@@ -22,6 +22,64 @@ __global__ void sort_keys_kernel(const double* __restrict__ data, long long n, i
   iota[i] = (int)i;
 }
 
+__device__ __forceinline__ unsigned long long spread3(unsigned long long x) {
+  x &= 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+// 63-bit Morton key of three projections (structure of arrays proj[3][n]), isotropic cells
+__global__ void morton_keys_kernel(const double* __restrict__ proj, long long n, double lo0, double lo1, double lo2,
+                                   double inv_cell, unsigned long long* __restrict__ keys, int* __restrict__ iota) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double lo[3] = {lo0, lo1, lo2};
+  unsigned long long key = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    double q = (proj[(long long)a * n + i] - lo[a]) * inv_cell;
+    q = q < 0.0 ? 0.0 : (q > 2097151.0 ? 2097151.0 : q);
+    key |= spread3((unsigned long long)q) << (2 - a);
+  }
+  keys[i] = key;
+  iota[i] = (int)i;
+}
+
+// lo[t][a] / hi[t][a] = bounding box (3 projections) of the 128 points of work-order tile t;
+// pure padding tiles get lo = +inf, hi = -inf
+__global__ void tile_boxes_kernel(const double* __restrict__ proj, const int* __restrict__ perm, long long n,
+                                  long long ntiles, double* __restrict__ lo, double* __restrict__ hi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= ntiles) return;
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int j = lane; j < 128; j += 32) {
+    const long long i = t * 128 + j;
+    if (i < n) {
+      const long long src = perm ? perm[i] : i;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double v = proj[(long long)a * n + src];
+        mn[a] = fmin(mn[a], v);
+        mx[a] = fmax(mx[a], v);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fmin(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmax(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    if (lane == 0) { lo[t * 3 + a] = mn[a]; hi[t * 3 + a] = mx[a]; }
+  }
+}
+
 __global__ void invert_perm_kernel(const int* __restrict__ perm, long long n, int* __restrict__ inv) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) inv[perm[i]] = (int)i;
@@ -81,6 +139,36 @@ int pb200_argsort_col_f64(const double* data, long long n, int m, int col, int* 
   PB_CHECK(cub::DeviceRadixSort::SortPairs((void*)p, temp, kin, kout, iota, perm, (int)n, 0, 64, st));
   invert_perm_kernel<<<div_up(n, 256), 256, 0, st>>>(perm, n, inv);
   PB_CHECK_LAUNCH("invert_perm_kernel");
+  return 0;
+}
+
+// Morton (Z-curve) order of n points given three projections proj[3][n] (structure of arrays):
+// cell size 1/inv_cell, origin (lo0, lo1, lo2), 21 bits per axis.  Scratch as pb200_argsort_col_f64.
+int pb200_morton_order(const double* proj, long long n, double lo0, double lo1, double lo2, double inv_cell,
+                       int* perm, int* inv, void* scratch, long long scratch_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n >= 2147483647LL) { set_error_msg("pb200_morton_order: n too large"); return -1; }
+  if (scratch_bytes < pb200_argsort_scratch_bytes(n)) { set_error_msg("pb200_morton_order: scratch too small"); return -1; }
+  const size_t al = 256;
+  char* p = (char*)scratch;
+  unsigned long long* kin = (unsigned long long*)p;  p += ((size_t)n * 8 + al - 1) / al * al;
+  unsigned long long* kout = (unsigned long long*)p; p += ((size_t)n * 8 + al - 1) / al * al;
+  int* iota = (int*)p;                               p += ((size_t)n * 4 + al - 1) / al * al;
+  size_t temp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp, kin, kout, iota, perm, (int)n);
+  morton_keys_kernel<<<div_up(n, 256), 256, 0, st>>>(proj, n, lo0, lo1, lo2, inv_cell, kin, iota);
+  PB_CHECK_LAUNCH("morton_keys_kernel");
+  PB_CHECK(cub::DeviceRadixSort::SortPairs((void*)p, temp, kin, kout, iota, perm, (int)n, 0, 64, st));
+  invert_perm_kernel<<<div_up(n, 256), 256, 0, st>>>(perm, n, inv);
+  PB_CHECK_LAUNCH("invert_perm_kernel");
+  return 0;
+}
+
+// box_lo / box_hi [ntiles][3]
+int pb200_tile_boxes(const double* proj, const int* perm, long long n, long long ntiles, double* box_lo,
+                     double* box_hi, void* stream) {
+  tile_boxes_kernel<<<div_up(ntiles, 8), 256, 0, (cudaStream_t)stream>>>(proj, perm, n, ntiles, box_lo, box_hi);
+  PB_CHECK_LAUNCH("tile_boxes_kernel");
   return 0;
 }
 

@@ -3,25 +3,44 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from palantir_b200 import _device as dv, _device_core as dc, _native
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+n = 1_000_000
 rng = np.random.default_rng(0)
-# a thick noisy curve in 6-D, like the min-max scaled multiscale space
-t = np.sort(rng.random(n))
-data = np.stack([t, np.sin(3 * t) * 0.5 + 0.5, np.cos(5 * t) * 0.5 + 0.5, t ** 2, np.sqrt(t), 0.5 + 0.3 * np.sin(9 * t)], 1)
-data += rng.normal(size=data.shape) * 2e-3
-dev = dv.to_device(np.ascontiguousarray(data))
-perm, inv, work = dc.locality_order(dev)
-idx, dist, st = dc.knn_table_sorted(work, 30)
-g = dc.undirected_graph(idx, dist)
-src = dv.to_device(rng.choice(n, 1198, replace=False).astype(np.int64))
-lib = _native.load()
-mean_w = float(g.data.mean().item())
-print("arcs", g.nnz, "mean w", mean_w)
-for ctas in (4, 2, 1):
-    lib.pb200_sssp_set_ctas_per_sm(ctas)
-    for mult in (2.0, 4.0, 8.0, 16.0):
+if "--bench" in sys.argv:
+    # the benchmark's own graph: multiscale space of the synthetic 1M x 100 workload
+    import pandas as pd
+    from palantir_b200 import pipeline, utils
+    from palantir_b200.datasets import synth_branching
+    x, info = synth_branching(n, 100)
+    out = pipeline.run_device(dv.to_device(x), info["early"], list(info["terminals"].values()))
+    data_t = dc.minmax_scale(out["multiscale"])
+    perm, inv, work = dc.locality_order(data_t)
+    idx, dist, st = dc.knn_table_sorted(work, 30)
+    g = dc.undirected_graph(idx, dist)
+    src = dv.to_device(inv.cpu().numpy().astype(np.int64)[out["waypoints"]])
+    lib = _native.load()
+    mean_w = float(g.data.mean().item())
+    print("bench graph arcs", g.nnz, "mean w", mean_w)
+else:
+  pass
+if "--bench" not in sys.argv:
+    # a thick noisy curve in 6-D, like the min-max scaled multiscale space
+    t = np.sort(rng.random(n))
+    data = np.stack([t, np.sin(3 * t) * 0.5 + 0.5, np.cos(5 * t) * 0.5 + 0.5, t ** 2, np.sqrt(t), 0.5 + 0.3 * np.sin(9 * t)], 1)
+    data += rng.normal(size=data.shape) * 2e-3
+    dev = dv.to_device(np.ascontiguousarray(data))
+    perm, inv, work = dc.locality_order(dev)
+    idx, dist, st = dc.knn_table_sorted(work, 30)
+    g = dc.undirected_graph(idx, dist)
+    src = dv.to_device(rng.choice(n, 1198, replace=False).astype(np.int64))
+    lib = _native.load()
+    mean_w = float(g.data.mean().item())
+    print("arcs", g.nnz, "mean w", mean_w)
+for variant in (0, 2, 3, 4, 5, 6, 7):
+    lib.pb200_sssp_set_variant(variant)
+    lib.pb200_sssp_set_ctas_per_sm(4)
+    for mult in (4.0, 8.0):
         torch.cuda.synchronize(); t0 = time.time()
         D, stats = dc.sssp(g, src, delta=mult * mean_w, want_stats=True)
         torch.cuda.synchronize(); dt = time.time() - t0
         s = stats.double().mean(0).cpu().numpy()
-        print(f"ctas/SM {ctas} delta {mult}x: {dt*1e3:.1f} ms rounds {s[0]:.0f} relax/arcs {s[1]/g.nnz:.2f} advances {s[2]:.0f}", flush=True)
+        print(f"variant {variant} ctas {lib.pb200_sssp_num_ctas(1198)} delta {mult}x: {dt*1e3:.1f} ms rounds {s[0]:.0f} relax/arcs {s[1]/g.nnz:.2f} advances {s[2]:.0f}", flush=True)
