@@ -140,7 +140,7 @@ int pb200_csr_spmm_f32(const int* indptr, const int* indices, const double* vals
 int pb200_vec_mul(const double* a, const double* b, double* out, long long n, void* stream);
 /* V0 = w / |w|.  scratch: partial[n/2048+1], tmp[1] */
 int pb200_lanczos_init(const double* w, long long n, double* V0, double* partial, double* tmp, void* stream);
-/* Lanczos steps j0..j0+nsteps-1 with full (CGS2) re-orthogonalisation; alpha[j], beta[j+1], V[j+1] written.
+/* Lanczos steps j0..j0+nsteps-1 with full re-orthogonalisation (three-term recurrence + one Gram-Schmidt pass); alpha[j], beta[j+1], V[j+1] written.
  * scratch: w[n], h[j0+nsteps], partial[(j0+nsteps) * (n/2048+1)], tmp[1] */
 int pb200_lanczos_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
                         double* V, long long ldv, int j0, int nsteps, double* alpha, double* beta, double* w,

@@ -35,9 +35,38 @@ def zeros(shape, dtype):
 
 
 def to_device(a: np.ndarray) -> torch.Tensor:
-    """Host array -> device tensor (one H2D copy, through pinned staging for big arrays)."""
+    """Host array -> contiguous row-major device tensor (one H2D copy).  A Fortran-ordered matrix
+    (what ``DataFrame.values`` returns for a frame that owns its data) is uploaded as it lies in
+    memory and transposed on the device instead of being re-laid-out by the host first."""
+    a = np.asarray(a)
+    if a.ndim == 2 and not a.flags.c_contiguous and a.flags.f_contiguous:
+        t = torch.from_numpy(a.T).to(_dev(), non_blocking=False)       # [cols, rows], contiguous
+        return t.t().contiguous()
     t = torch.from_numpy(np.ascontiguousarray(a))
     return t.to(_dev(), non_blocking=False)
+
+
+_PIN_MIN_BYTES = 1 << 20
+
+
+def to_host(*tensors: torch.Tensor):
+    """Device tensors -> numpy arrays.  Large results go through page-locked buffers (DMA at PCIe
+    speed instead of a staged copy into freshly faulted pageable memory); the arrays returned own
+    their pinned buffers.  One synchronisation for the whole batch."""
+    outs, pending = [], False
+    for t in tensors:
+        t = t.contiguous()
+        if t.is_cuda and t.numel() * t.element_size() >= _PIN_MIN_BYTES:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            pending = True
+            outs.append(buf)
+        else:
+            outs.append(t.cpu())
+    if pending:
+        torch.cuda.current_stream().synchronize()
+    arrs = [o.numpy() for o in outs]
+    return arrs[0] if len(arrs) == 1 else arrs
 
 
 def round_up(x: int, m: int) -> int:
@@ -361,8 +390,8 @@ def csr_from_host(m) -> DeviceCSR:
 def csr_to_host(c: DeviceCSR, data: Optional[torch.Tensor] = None):
     from scipy.sparse import csr_matrix
 
-    vals = (c.data if data is None else data).cpu().numpy()
-    return csr_matrix((vals, c.indices.cpu().numpy(), c.indptr.cpu().numpy()), shape=(c.n, c.n))
+    vals, indices, indptr = to_host(c.data if data is None else data, c.indices, c.indptr)
+    return csr_matrix((vals, indices, indptr), shape=(c.n, c.n))
 
 
 # ---------------------------------------------------------------------------

@@ -227,7 +227,8 @@ def run_palantir(data, early_cell, terminal_states=None, knn: int = 30, num_wayp
 
     index = ms_data.index
     n = len(index)
-    ms_dev = dv.to_device(np.ascontiguousarray(ms_data.values, dtype=np.float64))
+    ms_vals = ms_data.values
+    ms_dev = dv.to_device(ms_vals if ms_vals.dtype == np.float64 else ms_vals.astype(np.float64))
     dev = dc.minmax_scale(ms_dev) if scale_components else ms_dev.clone()
 
     # boundary cells and the start cell (core.py:186-192)
@@ -272,12 +273,13 @@ def run_palantir(data, early_cell, terminal_states=None, knn: int = 30, num_wayp
     if perm is not None:
         fates_dev, ent_dev = dc.unpermute_rows(fates_dev, perm), dc.unpermute_rows(ent_dev, perm)
 
-    pseudotime = pd.Series(pt_dev.cpu().numpy(), index=index)
-    branch_probs = pd.DataFrame(fates_dev.cpu().numpy(), index=index, columns=term_labels)
+    pt_h, fates_h, ent_h = dv.to_host(pt_dev, fates_dev, ent_dev)
+    pseudotime = pd.Series(pt_h, index=index)
+    branch_probs = pd.DataFrame(fates_h, index=index, columns=term_labels)
     if branch_probs.shape[1] == 0:
         ent = pd.Series(0.0, index=index)      # scipy entropy of an empty row is 0 in the reference's apply
     else:
-        ent = pd.Series(ent_dev.cpu().numpy(), index=index)
+        ent = pd.Series(ent_h, index=index)
 
     pr_res = PResults(pseudotime, ent, branch_probs, waypoints)
 

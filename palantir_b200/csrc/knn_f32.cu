@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_candidates_kernel(const Kn
     const bool last = (kc == KCH - 1);
     const int klen = last ? p.k_tail : KNN_DK;
 #pragma unroll 1
-    for (int k0 = 0; k0 < klen; k0 += 4) {
+    for (int k0 = 0; k0 < klen; k0 += 4) {   // 4 steps per trip measured fastest (vs 8 or straight-line 16)
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const int k = k0 + kk;

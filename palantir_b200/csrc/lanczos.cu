@@ -9,9 +9,12 @@
 //
 // The recurrence runs on the device with no host round trip per step: alpha and
 // beta stay in device memory and every kernel reads the scalars it needs from
-// there.  Re-orthogonalisation is classical Gram-Schmidt applied twice (CGS2):
-// h = V^T w, w -= V h, all basis vectors read with coalesced row-contiguous
-// loads; all reductions are two-stage and deterministic (no FP atomics).
+// there.  Each step applies the three-term recurrence (w = S v_j - alpha_j v_j -
+// beta_j v_{j-1}) and then one full classical Gram-Schmidt pass against the whole
+// basis (h = V^T w, w -= V h): after the recurrence w is already of size beta_{j+1},
+// so the pass only removes round-off-level components and there is no cancellation
+// that would call for a second pass.  All basis vectors are read with coalesced
+// row-contiguous loads; all reductions are two-stage and deterministic (no FP atomics).
 #include "common.cuh"
 
 namespace pb200 {
@@ -171,6 +174,15 @@ __global__ void scale_by_norm_kernel(const double* __restrict__ w, const double*
   if (i < n) out[i] = b > 0.0 ? w[i] / b : 0.0;
 }
 
+// h2[0] = beta[j] (0 when j == 0), h2[1] = alpha[j]
+__global__ void recurrence_coeffs_kernel(const double* __restrict__ alpha, const double* __restrict__ beta, int j,
+                                         double* __restrict__ h2) {
+  if (threadIdx.x == 0) {
+    h2[0] = j > 0 ? beta[j] : 0.0;
+    h2[1] = alpha[j];
+  }
+}
+
 __global__ void vec_mul_kernel(const double* __restrict__ a, const double* __restrict__ b,
                                double* __restrict__ out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,19 +317,27 @@ int pb200_lanczos_steps(const int* indptr, const int* indices, const double* val
     const int m = j + 1;
     int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st);
     if (rc) return rc;
-    // CGS2 against V[0..j]; alpha_j = (first + second) projection on v_j
-    PB_CHECK(cudaMemsetAsync(alpha + j, 0, sizeof(double), st));
-    for (int pass = 0; pass < 2; ++pass) {
-      multi_dot_kernel<<<nblk, VB, 0, st>>>(V, ldv, m, w, n, partial);
-      PB_CHECK_LAUNCH("multi_dot_kernel");
-      reduce_partials_kernel<<<m, 256, 0, st>>>(partial, nblk, m, h, nullptr);
-      PB_CHECK_LAUNCH("reduce_partials_kernel");
-      // alpha_j += h[j]
-      reduce_partials_kernel<<<1, 32, 0, st>>>(h + j, 1, 1, tmp, alpha + j);
-      PB_CHECK_LAUNCH("reduce_partials_kernel(alpha)");
-      multi_axpy_kernel<<<nblk, VB, sizeof(double) * m, st>>>(V, ldv, m, h, w, n);
-      PB_CHECK_LAUNCH("multi_axpy_kernel");
-    }
+    // three-term recurrence: alpha_j = v_j . w;  w -= alpha_j v_j + beta_j v_{j-1}
+    multi_dot_kernel<<<nblk, VB, 0, st>>>(V + (long long)j * ldv, ldv, 1, w, n, partial);
+    PB_CHECK_LAUNCH("multi_dot_kernel(alpha)");
+    reduce_partials_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, alpha + j, nullptr);
+    PB_CHECK_LAUNCH("reduce_partials_kernel(alpha)");
+    recurrence_coeffs_kernel<<<1, 32, 0, st>>>(alpha, beta, j, h);
+    PB_CHECK_LAUNCH("recurrence_coeffs_kernel");
+    if (j > 0)
+      multi_axpy_kernel<<<nblk, VB, sizeof(double) * 2, st>>>(V + (long long)(j - 1) * ldv, ldv, 2, h, w, n);
+    else
+      multi_axpy_kernel<<<nblk, VB, sizeof(double) * 1, st>>>(V, ldv, 1, h + 1, w, n);
+    PB_CHECK_LAUNCH("multi_axpy_kernel(recurrence)");
+    // one full Gram-Schmidt pass against V[0..j]; its v_j component corrects alpha_j
+    multi_dot_kernel<<<nblk, VB, 0, st>>>(V, ldv, m, w, n, partial);
+    PB_CHECK_LAUNCH("multi_dot_kernel");
+    reduce_partials_kernel<<<m, 256, 0, st>>>(partial, nblk, m, h, nullptr);
+    PB_CHECK_LAUNCH("reduce_partials_kernel");
+    reduce_partials_kernel<<<1, 32, 0, st>>>(h + j, 1, 1, tmp, alpha + j);
+    PB_CHECK_LAUNCH("reduce_partials_kernel(alpha)");
+    multi_axpy_kernel<<<nblk, VB, sizeof(double) * m, st>>>(V, ldv, m, h, w, n);
+    PB_CHECK_LAUNCH("multi_axpy_kernel");
     rc = nrm2_into(w, n, partial, tmp, st);
     if (rc) return rc;
     scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V + (long long)(j + 1) * ldv, n, beta + j + 1);

@@ -67,7 +67,7 @@ def compute_kernel(data, knn: int = 30, alpha: float = 0, pca_key: str = "X_pca"
     if knn is None or int(knn) <= 0:
         raise ValueError("knn must be a positive integer")
     values = data_df.values if isinstance(data_df, pd.DataFrame) else np.asarray(data_df)
-    kern = _compute_kernel_device(np.ascontiguousarray(values), int(knn), float(alpha))
+    kern = _compute_kernel_device(values, int(knn), float(alpha))
     kernel = dv.csr_to_host(kern)
     kernel._pb200_device = kern          # lets run_diffusion_maps skip the re-upload
     if is_anndata(data):
@@ -106,7 +106,7 @@ def diffusion_maps_from_kernel(kernel: csr_matrix, n_components: int = 10,
         kern = dv.csr_from_host(kernel)
     tvals, lam, U = _diffusion_maps_device(kern, n_components, seed)
     T = dv.csr_to_host(kern, tvals)
-    return {"T": T, "EigenVectors": pd.DataFrame(U.cpu().numpy()), "EigenValues": pd.Series(lam)}
+    return {"T": T, "EigenVectors": pd.DataFrame(dv.to_host(U), copy=False), "EigenValues": pd.Series(lam)}
 
 
 def run_diffusion_maps(data, n_components: int = 10, knn: int = 30, alpha: float = 0,
