@@ -84,7 +84,7 @@ CPU_SAMPLE_CELLS, CPU_SAMPLE_WP = 12000, 150
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     n_s, wp = CPU_SAMPLE_CELLS, CPU_SAMPLE_WP
     for _ in range(args.warmup):
         _cpu_sample(n_s, args.pcs, wp)
@@ -103,7 +103,7 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    return line
 
 
 # --------------------------------------------------------------------------------------
@@ -243,8 +243,9 @@ def run_gpu_arm(args):
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
-        return
+        return None
 
     # ---- rooflines ----
     peaks = {}
@@ -323,6 +324,15 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def _quiet_stdout():
+    """Route everything the run writes to fd 1 (NCCL's version banner, library prints) to stderr;
+    returns a file object on the real stdout for the single JSON line."""
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w")
+    return real
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -333,10 +343,11 @@ def main():
     ap.add_argument("--pcs", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_gpu_arm(args)
+    out = _quiet_stdout()
+    line = run_reference_arm(args) if args.impl == "reference" else run_gpu_arm(args)
+    if line is not None:
+        out.write(json.dumps(line) + "\n")
+        out.flush()
 
 
 if __name__ == "__main__":
