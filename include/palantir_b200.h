@@ -70,11 +70,23 @@ int pb200_knn_candidates_f32(const float* xt, long long n_pad, const float* yn, 
 /* FP64 re-rank with the reference's expanded-form distance; candidates are work-order indices, x is the
  * input matrix (row of work point j = perm[j]; perm may be NULL); out_idx [nq][k] holds INPUT-order indices,
  * rows are in work order, ascending by (distance, input index); flag[nq] = 1 where the FP32 error bound
- * cannot certify the row; n_flagged[1]. */
+ * cannot certify the row (|s32 - s| <= 2^-24 (eps_coef |x||y| + 4 R^2); eps_coef = 2 (d + 8) for the FP32
+ * kernel); n_flagged[1]. */
 int pb200_knn_rerank_f64(const void* x, int is_f64, const int* perm, const double* xn64, const double* xcn,
                          const double* rmax2, long long n, int d, int q0, int nq, const int* cand,
-                         const float* thr32, int k_keep, int k, int* out_idx, double* out_dist,
+                         const float* thr32, int k_keep, int k, double eps_coef, int* out_idx, double* out_dist,
                          unsigned char* flag, int* n_flagged, void* stream);
+
+/* Tensor-core (tcgen05, 3xTF32) candidate generation: same outputs as pb200_knn_candidates_f32 for d <= 128.
+ * xtc: TF32 hi/lo operand copy (pb200_knn_tc_operand_floats floats) written by pb200_knn_prepare_tc; q0 % 128 == 0;
+ * lists: ceil(nq/128)*128*64 64-bit words.  The re-rank certificate uses eps_coef = 2 (16 + 4 * 3 * ceil(d/8)). */
+long long pb200_knn_tc_operand_floats(long long n_pad, int d);
+int pb200_knn_prepare_tc(const void* x, int is_f64, long long n, int d, long long n_pad, const double* mean,
+                         const int* perm, float* xtc, void* stream);
+int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, const double* xcn,
+                            const double* box_lo, const double* box_hi, int q0, int nq, int d, int k_keep,
+                            unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
+                            unsigned long long* tiles_visited, void* stream);
 
 /* rows_out[0..counter) = indices (relative to q0) of flagged rows. */
 int pb200_knn_flagged_rows(const unsigned char* flag, int nq, int* rows_out, int* counter, void* stream);
@@ -176,6 +188,16 @@ int pb200_sssp_set_variant(int v);
 int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
                      int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,
                      void* stream);
+
+/* Arc-record form of the same search: arcs[nnz + 64] of {int v; int indptr[v]; double w} (16 B each); work lists
+ * hold (vertex, row start) pairs.  scratch: q[n_ctas*3*n] int pairs, bits[n_ctas*3*ceil(n/32)] uint32 with
+ * n_ctas = pb200_sssp_arcrec_ctas(n_sources, threads); threads in {128, 256, 512} per source. */
+int pb200_sssp_build_arcs(const int* indptr, const int* indices, const double* wts, long long nnz, void* arcs,
+                          void* stream);
+int pb200_sssp_arcrec_ctas(int n_sources, int threads);
+int pb200_sssp_multi_arcrec(const int* indptr, const void* arcs, long long n, const long long* sources,
+                            int n_sources, double delta, int threads, double* D, void* q, unsigned int* bits,
+                            long long* stats, void* stream);
 
 /* ---- pseudotime refinement and projection (core.py:368-397, 225-230) ---- */
 int pb200_sum_pow_f64(const double* x, long long count, double shift, int power, double* partial, double* out,

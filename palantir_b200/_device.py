@@ -7,6 +7,7 @@ are assembled by ``utils.py``.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -110,6 +111,8 @@ def flush_profile():
 # kNN
 # ---------------------------------------------------------------------------
 KNN_MAX_KEEP = 48
+# candidate-generation engine: "simt" (FP32 FFMA kernel) or "tc" (tcgen05 3xTF32 kernel, d <= 128)
+KNN_ENGINE = os.environ.get("PB200_KNN_ENGINE", "simt")
 
 
 def sklearn_uses_brute(n: int, d: int, n_neighbors: int) -> bool:
@@ -130,6 +133,8 @@ class KnnPrep:
     rmax2: torch.Tensor
     box_lo: Optional[torch.Tensor]    # [ntiles, 3] projection boxes of the 128-point tiles
     box_hi: Optional[torch.Tensor]
+    xtc: Optional[torch.Tensor]       # TF32 hi/lo operand copy for the tensor-core engine
+    mean: torch.Tensor
     n: int
     d: int
     d_pad: int
@@ -204,7 +209,12 @@ def knn_prepare(x: torch.Tensor, prune: bool = True) -> KnnPrep:
     xn64 = empty((n,), F64)
     rmax2 = empty((1,), F64)
     call("pb200_knn_prepare", x, is64, n, d, d_pad, ld, mean, perm, xt, yn, xcn, xn64, rmax2)
-    return KnnPrep(x, perm, xt, yn, xcn, xn64, rmax2, box_lo, box_hi, n, d, d_pad, ld)
+    xtc = None
+    if KNN_ENGINE == "tc" and d <= 128:
+        nfl = int(_native.load().pb200_knn_tc_operand_floats(ld, d))
+        xtc = empty((nfl,), F32)
+        call("pb200_knn_prepare_tc", x, is64, n, d, ld, mean, perm, xtc)
+    return KnnPrep(x, perm, xt, yn, xcn, xn64, rmax2, box_lo, box_hi, xtc, mean, n, d, d_pad, ld)
 
 
 def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
@@ -235,18 +245,26 @@ def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
     thr = empty((nq,), F32)
     lists = empty((round_up(nq, 256) * 64,), I64)
     visited = zeros((1,), I64)
+    use_tc = prep.xtc is not None
     with stage("knn_candidates"):
-        call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.yn, prep.xcn, prep.box_lo, prep.box_hi, q0, nq,
-             prep.d, prep.d_pad, k_keep, lists, cand, score, thr, visited)
+        if use_tc:
+            call("pb200_knn_candidates_tc", prep.xtc, prep.ld, prep.yn, prep.xcn, prep.box_lo, prep.box_hi, q0, nq,
+                 prep.d, k_keep, lists, cand, score, thr, visited)
+        else:
+            call("pb200_knn_candidates_f32", prep.xt, prep.ld, prep.yn, prep.xcn, prep.box_lo, prep.box_hi, q0, nq,
+                 prep.d, prep.d_pad, k_keep, lists, cand, score, thr, visited)
     del lists
+    eps_coef = 2.0 * (16 + 4 * 3 * ((d + 7) // 8)) if use_tc else 2.0 * (d + 8)
+    stats["engine"] = "tc" if use_tc else "simt"
     flag = empty((nq,), U8)
     n_flagged = empty((1,), I32)
     with stage("knn_rerank"):
         call("pb200_knn_rerank_f64", prep.x, is64, prep.perm, prep.xn64, prep.xcn, prep.rmax2, n, d, q0, nq, cand,
-             thr, k_keep, k, out_idx, out_dist, flag, n_flagged)
+             thr, k_keep, k, eps_coef, out_idx, out_dist, flag, n_flagged)
     nf = int(n_flagged.item())
     stats["flagged"] = nf
-    stats["tiles_visited_frac"] = float(visited.item()) / (max(1, (nq + 255) // 256) * (prep.ld // 128))
+    cta_rows = 128 if use_tc else 256
+    stats["tiles_visited_frac"] = float(visited.item()) / (max(1, (nq + cta_rows - 1) // cta_rows) * (prep.ld // 128))
     if nf > 0:
         rows = empty((nq,), I32)
         counter = empty((1,), I32)

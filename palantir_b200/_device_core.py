@@ -135,6 +135,20 @@ def unreachable_count(g: dv.DeviceCSR, start: int):
     return int(count.item()), label
 
 
+SSSP_MODE = "arcrec"       # "arcrec" (arc records + prefetch) or "csr" (plain CSR kernel variants)
+SSSP_THREADS = None        # None: chosen from the number of sources
+
+
+def _sssp_threads(n_sources: int) -> int:
+    """Threads per source: as many as possible while every source stays resident (one wave)."""
+    if SSSP_THREADS is not None:
+        return SSSP_THREADS
+    for t in (512, 256):
+        if n_sources <= (1280 // t) * 148:
+            return t
+    return 128
+
+
 def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, want_stats: bool = False):
     """D[S, n] shortest-path distances from each source (unreachable = +inf)."""
     n, S = g.n, int(sources.numel())
@@ -144,12 +158,23 @@ def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, 
             delta = 1.0
     D = empty((S, n), F64)
     lib = _native.load()
+    stats = zeros((S, 3), I64) if want_stats else None
+    nwords = (n + 31) // 32
+    if SSSP_MODE == "arcrec":
+        threads = _sssp_threads(S)
+        n_ctas = lib.pb200_sssp_arcrec_ctas(S, threads)
+        arcs = empty(((g.nnz + 64) * 2,), F64)                     # 16-byte records
+        with stage("sssp"):
+            call("pb200_sssp_build_arcs", g.indptr, g.indices, g.data, g.nnz, arcs)
+            q = empty((n_ctas * 3 * n * 2,), I32)
+            bits = empty((n_ctas * 3 * nwords,), U32)
+            call("pb200_sssp_multi_arcrec", g.indptr, arcs, n, sources, S, float(delta), threads, D, q, bits, stats)
+        return D, stats
     n_ctas = lib.pb200_sssp_num_ctas(S)
     q = empty((n_ctas * 3 * n,), I32)
-    marks = empty((n_ctas * 3 * ((n + 31) // 32),), U32)
-    stats = zeros((S, 3), I64) if want_stats else None
+    bits = empty((n_ctas * 3 * nwords,), U32)
     with stage("sssp"):
-        call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, marks, stats)
+        call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, bits, stats)
     return D, stats
 
 

@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(
     const T* __restrict__ x, const int* __restrict__ perm, const double* __restrict__ xn64,
     const double* __restrict__ xcn, const double* __restrict__ rmax2, long long n, int d, int q0, int nq,
     const int* __restrict__ cand,
-    const float* __restrict__ thr32, int kk, int k, int* __restrict__ out_idx, double* __restrict__ out_dist,
+    const float* __restrict__ thr32, int kk, int k, double eps_coef, int* __restrict__ out_idx,
+    double* __restrict__ out_dist,
     unsigned char* __restrict__ flag, int* __restrict__ n_flagged) {
   extern __shared__ double xs[];  // [4][d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,7 +83,10 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(
   const double xc = xcn[i];
   const double R2 = *rmax2;
   const double u = 5.9604644775390625e-08;  // 2^-24
-  const double eps_base = 1.05 * u * (2.0 * (d + 8) * sqrt(xc * R2) + 4.0 * R2);
+  // |s32 - s| <= u (eps_coef |x||y| + 4 R^2): eps_coef = 2 (d + 8) for the FP32 FMA chain of the SIMT
+  // kernel, 2 (16 + 4 n_mma) for the 3xTF32 tensor-core kernel (operand split, dropped lo.lo term and
+  // up to 2 ulp of accumulation error per MMA)
+  const double eps_base = 1.05 * u * (eps_coef * sqrt(xc * R2) + 4.0 * R2);
   bool bad = false;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -200,7 +204,7 @@ extern "C" {
 
 int pb200_knn_rerank_f64(const void* x, int is_f64, const int* perm, const double* xn64, const double* xcn,
                          const double* rmax2, long long n, int d, int q0, int nq, const int* cand,
-                         const float* thr32, int k_keep, int k, int* out_idx, double* out_dist,
+                         const float* thr32, int k_keep, int k, double eps_coef, int* out_idx, double* out_dist,
                          unsigned char* flag, int* n_flagged, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (k_keep > 64 || k > k_keep || k < 1) {
@@ -213,12 +217,12 @@ int pb200_knn_rerank_f64(const void* x, int is_f64, const int* perm, const doubl
   const size_t smem = sizeof(double) * 4 * (size_t)d;
   if (is_f64)
     knn_rerank_kernel<double><<<blocks, 128, smem, st>>>((const double*)x, perm, xn64, xcn, rmax2, n, d, q0, nq,
-                                                          cand, thr32, k_keep, k, out_idx, out_dist, flag,
-                                                          n_flagged);
+                                                          cand, thr32, k_keep, k, eps_coef, out_idx, out_dist,
+                                                          flag, n_flagged);
   else
     knn_rerank_kernel<float><<<blocks, 128, smem, st>>>((const float*)x, perm, xn64, xcn, rmax2, n, d, q0, nq,
-                                                         cand, thr32, k_keep, k, out_idx, out_dist, flag,
-                                                         n_flagged);
+                                                         cand, thr32, k_keep, k, eps_coef, out_idx, out_dist,
+                                                         flag, n_flagged);
   PB_CHECK_LAUNCH("knn_rerank_kernel");
   return 0;
 }

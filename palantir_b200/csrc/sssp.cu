@@ -395,6 +395,212 @@ __global__ void __launch_bounds__(THREADS) sssp_group_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Arc-record variant.  Each arc carries the row start of its head vertex, {v, indptr[v], w}
+// (16 B), and the work lists hold (vertex, row start) pairs.  A popped vertex can therefore issue
+// its arc loads at once -- in parallel with its own distance and row end instead of after an
+// indptr lookup -- and a push prefetches the pushed vertex's arcs into L2, so that the next
+// round finds them there instead of in HBM.  One dependent memory level fewer per round, and the
+// longest one (HBM) shortened: the round latency is what bounds this kernel.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) SsspArc {
+  int v;
+  int beg;
+  double w;
+};
+
+__global__ void sssp_build_arcs_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
+                                       const double* __restrict__ wts, long long nnz, long long nnz_pad,
+                                       SsspArc* __restrict__ arcs) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz_pad) return;
+  SsspArc a;
+  if (e < nnz) { a.v = indices[e]; a.beg = indptr[a.v]; a.w = wts[e]; }
+  else { a.v = 0; a.beg = 0; a.w = INFINITY; }
+  arcs[e] = a;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
+    const int* __restrict__ indptr, const SsspArc* __restrict__ arcs, int n, const long long* __restrict__ sources,
+    int n_sources, double delta, double* __restrict__ D, int2* __restrict__ q_all,
+    unsigned int* __restrict__ bits_all, long long* __restrict__ stats) {
+  constexpr int LPV = 8;
+  constexpr int NW = THREADS / 32;
+  constexpr int NG = THREADS / LPV;
+  __shared__ int s_cnt[2];
+  __shared__ int s_cnt_far;
+  __shared__ double s_thr;
+  __shared__ double s_red[NW];
+  __shared__ int s_wtot[NW];
+  __shared__ int s_wtot2[NW];
+  __shared__ int s_base_keep, s_base_near;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int grp = tid / LPV, sub = tid % LPV;
+  int2* qbuf[2];
+  qbuf[0] = q_all + (size_t)blockIdx.x * 3 * (size_t)n;
+  qbuf[1] = qbuf[0] + n;
+  int2* far = qbuf[1] + n;
+  const int nwords = (n + 31) >> 5;
+  unsigned int* bnear[2];
+  bnear[0] = bits_all + (size_t)blockIdx.x * 3 * (size_t)nwords;
+  bnear[1] = bnear[0] + nwords;
+  unsigned int* bfar = bnear[1] + nwords;
+
+  for (int s = blockIdx.x; s < n_sources; s += gridDim.x) {
+    double* dist = D + (size_t)s * (size_t)n;
+    const int src = (int)sources[s];
+    for (int i = tid; i < n; i += THREADS) dist[i] = INFINITY;
+    for (int i = tid; i < 3 * nwords; i += THREADS) bnear[0][i] = 0u;
+    __syncthreads();
+    int p = 0;
+    if (tid == 0) {
+      dist[src] = 0.0;
+      qbuf[0][0] = make_int2(src, indptr[src]);
+      s_cnt[0] = 1; s_cnt[1] = 0; s_cnt_far = 0;
+      s_thr = delta;
+    }
+    __syncthreads();
+    long long rounds = 0, relax = 0, advances = 0;
+
+    for (;;) {
+      for (;;) {
+        const int cnt = s_cnt[p];
+        if (cnt == 0) break;
+        ++rounds;
+        const double thr = s_thr;
+        const int2* qa = qbuf[p];
+        int2* qb = qbuf[p ^ 1];
+        unsigned int* bcur = bnear[p];
+        unsigned int* bnext = bnear[p ^ 1];
+        for (int i = grp; i < cnt; i += NG) {
+          const int2 ub = qa[i];
+          const int u = ub.x, beg = ub.y;
+          if (sub == 0) atomicAnd(&bcur[u >> 5], ~(1u << (u & 31)));   // popped
+          // level 1: own distance, row end and the first 32 arcs, all independent
+          SsspArc ar[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ar[k] = arcs[beg + sub + k * LPV];      // padded: always in bounds
+          const double du = __ldcg(dist + u);
+          const int end = indptr[u + 1];
+          for (int e0 = beg + sub;;) {
+            bool ok[4];
+            double nd[4], dv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ok[k] = e0 + k * LPV < end;
+              nd[k] = du + ar[k].w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dv[k] = ok[k] ? __ldcg(dist + ar[k].v) : 0.0;     // level 2
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (ok[k] && nd[k] < dv[k]) {
+                const int v = ar[k].v;
+                const double old = atomic_min_pos_f64(dist + v, nd[k]);                     // level 3
+                if (nd[k] < old) {
+                  const unsigned int bit = 1u << (v & 31);
+                  if (nd[k] < thr) {
+                    if (!(atomicOr(&bnext[v >> 5], bit) & bit)) {                           // level 4
+                      qb[atomicAdd(&s_cnt[p ^ 1], 1)] = make_int2(v, ar[k].beg);
+                      const char* row = reinterpret_cast<const char*>(arcs + ar[k].beg);
+                      prefetch_l2(row); prefetch_l2(row + 128); prefetch_l2(row + 256);
+                      prefetch_l2(row + 384); prefetch_l2(row + 512);
+                    }
+                  } else {
+                    if (!(atomicOr(&bfar[v >> 5], bit) & bit)) far[atomicAdd(&s_cnt_far, 1)] = make_int2(v, ar[k].beg);
+                  }
+                }
+              }
+            }
+            e0 += 4 * LPV;
+            if (e0 - sub >= end) break;                 // uniform within the group
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ar[k] = arcs[e0 + k * LPV];
+          }
+          if (sub == 0) relax += end - beg;
+        }
+        __syncthreads();
+        if (tid == 0) s_cnt[p] = 0;
+        p ^= 1;
+        __syncthreads();
+      }
+      // ---------------- advance the threshold ----------------
+      const int nfar = s_cnt_far;
+      if (nfar == 0) break;
+      ++advances;
+      double mn = INFINITY;
+      for (int i = tid; i < nfar; i += THREADS) mn = fmin(mn, __ldcg(dist + far[i].x));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      if (lane == 0) s_red[warp] = mn;
+      __syncthreads();
+      if (tid == 0) {
+        double m2 = INFINITY;
+        for (int w = 0; w < NW; ++w) m2 = fmin(m2, s_red[w]);
+        s_thr = m2 + delta;
+        s_base_keep = 0;
+        s_base_near = 0;
+      }
+      __syncthreads();
+      const double thr2 = s_thr;
+      int2* qa = qbuf[p];
+      unsigned int* bcur = bnear[p];
+      for (int c0 = 0; c0 < nfar; c0 += THREADS) {
+        const int i = c0 + tid;
+        int2 vb = make_int2(-1, 0);
+        bool to_near = false, keep = false;
+        if (i < nfar) {
+          vb = far[i];
+          to_near = __ldcg(dist + vb.x) < thr2;
+          keep = !to_near;
+        }
+        const unsigned mk = __ballot_sync(0xffffffffu, keep);
+        const unsigned mnr = __ballot_sync(0xffffffffu, to_near);
+        if (lane == 0) { s_wtot[warp] = __popc(mk); s_wtot2[warp] = __popc(mnr); }
+        __syncthreads();
+        int offk = 0, offn = 0;
+        for (int w = 0; w < warp; ++w) { offk += s_wtot[w]; offn += s_wtot2[w]; }
+        const int bk = s_base_keep, bn = s_base_near;
+        __syncthreads();
+        if (keep) far[bk + offk + __popc(mk & ((1u << lane) - 1u))] = vb;
+        if (to_near) {
+          qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = vb;
+          atomicAnd(&bfar[vb.x >> 5], ~(1u << (vb.x & 31)));
+          atomicOr(&bcur[vb.x >> 5], 1u << (vb.x & 31));
+          prefetch_l2(arcs + vb.y);
+        }
+        if (tid == THREADS - 1) {
+          s_base_keep = bk + offk + __popc(mk);
+          s_base_near = bn + offn + __popc(mnr);
+        }
+        __syncthreads();
+      }
+      if (tid == 0) { s_cnt_far = s_base_keep; s_cnt[p] = s_base_near; }
+      __syncthreads();
+    }
+    if (stats) {
+      double r = (double)relax;
+      r = warp_sum(r);
+      if (lane == 0) s_red[warp] = r;
+      __syncthreads();
+      if (tid == 0) {
+        double tot = 0;
+        for (int w = 0; w < NW; ++w) tot += s_red[w];
+        stats[(size_t)s * 3 + 0] = rounds;
+        stats[(size_t)s * 3 + 1] = (long long)tot;
+        stats[(size_t)s * 3 + 2] = advances;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Variant with one WARP per frontier vertex (lanes = arcs) and a bit-clearing pass per round.
 __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
 
@@ -605,6 +811,47 @@ int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, l
     sssp_warp_kernel<<<grid, SSSP_THREADS, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources,
                                                                     n_sources, delta, D, q, bits, stats);
   PB_CHECK_LAUNCH("sssp_kernel");
+  return 0;
+}
+
+// Arc records {v, indptr[v], w} (16 B each, nnz + 64 entries) for pb200_sssp_multi_arcrec.
+int pb200_sssp_build_arcs(const int* indptr, const int* indices, const double* wts, long long nnz, void* arcs,
+                          void* stream) {
+  const long long pad = nnz + 64;
+  sssp_build_arcs_kernel<<<div_up(pad, 256), 256, 0, (cudaStream_t)stream>>>(indptr, indices, wts, nnz, pad,
+                                                                           (SsspArc*)arcs);
+  PB_CHECK_LAUNCH("sssp_build_arcs_kernel");
+  return 0;
+}
+
+// Number of resident CTAs for the arc-record kernel with `threads` (128, 256 or 512) threads per source.
+int pb200_sssp_arcrec_ctas(int n_sources, int threads) {
+  const int per_sm = 1280 / threads > 0 ? 1280 / threads : 1;      // 48 registers per thread
+  const int cap = per_sm * kSMs;
+  return n_sources < cap ? n_sources : cap;
+}
+
+// Same result as pb200_sssp_multi from arc records.  scratch: q[n_ctas*3*n] pairs of int (8 B each),
+// bits[n_ctas*3*ceil(n/32)] uint32 with n_ctas = pb200_sssp_arcrec_ctas(n_sources, threads).
+int pb200_sssp_multi_arcrec(const int* indptr, const void* arcs, long long n, const long long* sources,
+                            int n_sources, double delta, int threads, double* D, void* q, unsigned int* bits,
+                            long long* stats, void* stream) {
+  if (n_sources <= 0) return 0;
+  if (n >= 1073741823LL) { set_error_msg("pb200_sssp_multi_arcrec: n too large"); return -1; }
+  if (!(delta > 0.0)) { set_error_msg("pb200_sssp_multi_arcrec: delta must be > 0"); return -1; }
+  const int grid = pb200_sssp_arcrec_ctas(n_sources, threads);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (threads == 128)
+    sssp_arcrec_kernel<128><<<grid, 128, 0, st>>>(indptr, (const SsspArc*)arcs, (int)n, sources, n_sources, delta, D,
+                                                  (int2*)q, bits, stats);
+  else if (threads == 256)
+    sssp_arcrec_kernel<256><<<grid, 256, 0, st>>>(indptr, (const SsspArc*)arcs, (int)n, sources, n_sources, delta, D,
+                                                  (int2*)q, bits, stats);
+  else if (threads == 512)
+    sssp_arcrec_kernel<512><<<grid, 512, 0, st>>>(indptr, (const SsspArc*)arcs, (int)n, sources, n_sources, delta, D,
+                                                  (int2*)q, bits, stats);
+  else { set_error_msg("pb200_sssp_multi_arcrec: threads must be 128, 256 or 512"); return -1; }
+  PB_CHECK_LAUNCH("sssp_arcrec_kernel");
   return 0;
 }
 

@@ -35,12 +35,23 @@ if "--bench" not in sys.argv:
     lib = _native.load()
     mean_w = float(g.data.mean().item())
     print("arcs", g.nnz, "mean w", mean_w)
-for variant in (0, 2, 3, 4, 5, 6, 7):
-    lib.pb200_sssp_set_variant(variant)
-    lib.pb200_sssp_set_ctas_per_sm(4)
+def run(tag, mult=4.0, nsrc=None):
+    sr = src if nsrc is None else src[:nsrc].contiguous()
+    torch.cuda.synchronize(); t0 = time.time()
+    D, stats = dc.sssp(g, sr, delta=mult * mean_w, want_stats=True)
+    torch.cuda.synchronize(); dt = time.time() - t0
+    s = stats.double().mean(0).cpu().numpy()
+    print(f"{tag} sources {sr.numel()} delta {mult}x: {dt*1e3:.1f} ms rounds {s[0]:.0f} relax/arcs {s[1]/g.nnz:.2f} advances {s[2]:.0f}", flush=True)
+    return D
+dc.SSSP_MODE = "csr"; lib.pb200_sssp_set_variant(4)
+Dref = run("csr v4 (128 thr)")
+run("csr v4 (128 thr)", nsrc=150)
+dc.SSSP_MODE = "arcrec"
+for thr in (128, 256, 512):
+    dc.SSSP_THREADS = thr
     for mult in (4.0, 8.0):
-        torch.cuda.synchronize(); t0 = time.time()
-        D, stats = dc.sssp(g, src, delta=mult * mean_w, want_stats=True)
-        torch.cuda.synchronize(); dt = time.time() - t0
-        s = stats.double().mean(0).cpu().numpy()
-        print(f"variant {variant} ctas {lib.pb200_sssp_num_ctas(1198)} delta {mult}x: {dt*1e3:.1f} ms rounds {s[0]:.0f} relax/arcs {s[1]/g.nnz:.2f} advances {s[2]:.0f}", flush=True)
+        D = run(f"arcrec {thr} thr", mult)
+    print("   identical to csr result:", bool(torch.equal(D, Dref)))
+dc.SSSP_THREADS = None
+for ns in (599, 300, 150):
+    run("arcrec auto", nsrc=ns)
