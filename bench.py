@@ -228,7 +228,9 @@ def run_gpu_arm(args):
     barrier()
     t0 = time.perf_counter()
     n_e2e = max(1, min(args.steps, 2))
+    res = msd = pr = None
     for _ in range(n_e2e):
+        res = msd = pr = None                  # release the previous step's (page-locked) result buffers
         res, msd, pr = api_step()
     barrier()
     e2e_s = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
@@ -265,8 +267,33 @@ def run_gpu_arm(args):
     nq_rank = -(-n // world)
     knn_ms = prof.get("knn_candidates", float("nan"))
     knn_alg_tf = 2.0 * nq_rank * n * d / knn_ms / 1e9 if knn_ms == knn_ms else None
-    visited = (out["knn"] or {}).get("tiles_visited_frac") or 1.0
-    knn_tf = knn_alg_tf * visited if knn_alg_tf else None          # FLOPs actually executed
+    kinfo = out["knn"] or {}
+    visited = kinfo.get("tiles_visited_frac") or 1.0
+    engine = kinfo.get("engine", "simt")
+    if engine == "tc":
+        # executed tensor work: three TF32 MMAs per product, coordinates padded to a multiple of 8
+        d8 = -(-d // 8) * 8
+        knn_tf = 3.0 * 2.0 * nq_rank * n * d8 * visited / knn_ms / 1e9 if knn_alg_tf else None
+        knn_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+        knn_roof = {"bound": "tensor", "kernel": "knn_candidates_tc_kernel (tcgen05.mma kind::tf32, 3xTF32 split)",
+                    "achieved": knn_tf, "peak": knn_peak, "unit": "TFLOP/s", "frac": knn_tf / knn_peak if knn_tf else None,
+                    "traffic": None,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the BF16 rate; of measured)"
+                                    if "bf16_tflops" in peaks else "B200_PROFILING.md fallback 1590/2 TF/s (of fallback)"),
+                    "algorithmic": "3 x 2*Nq*Nr*d8 TF32 FLOP per launch x fraction of 128x128 tiles visited (exact "
+                                   "projection pruning skips the rest); 'effective' = 2*Nq*Nr*d / time, all tiles counted",
+                    "tiles_visited_frac": visited, "effective_tflops": knn_alg_tf, "ms_per_launch": knn_ms,
+                    "fp32_simt_probe_tflops": fp32_peak}
+    else:
+        knn_tf = knn_alg_tf * visited if knn_alg_tf else None          # FLOPs actually executed
+        knn_roof = {"bound": "fp32 (SIMT FFMA; schema value would be 'tensor')", "kernel": "knn_candidates_kernel",
+                    "achieved": knn_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": (knn_tf / fp32_peak) if knn_tf else None, "traffic": None,
+                    "peak_source": "FFMA probe pb200_fma_peak_f32 timed in this run (MEASURED_PEAKS.json has no FP32 "
+                                   "figure)",
+                    "algorithmic": "2*Nq*Nr*d FLOP per launch x fraction of 256x128 tiles visited (exact projection "
+                                   "pruning skips the rest); 'effective' counts the skipped tiles too",
+                    "tiles_visited_frac": visited, "effective_tflops": knn_alg_tf, "ms_per_launch": knn_ms}
     # SpMV timed alone on the symmetric operator of the last step
     kd = out["kernel"]
     xs = torch.rand(n, dtype=torch.float64, device="cuda")
@@ -304,13 +331,7 @@ def run_gpu_arm(args):
                 "ms_per_step": e2e_sec * 1e3, "steps": n_e2e},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "fp32 (SIMT FFMA; schema value would be 'tensor')", "kernel": "knn_candidates_kernel",
-                     "achieved": knn_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": (knn_tf / fp32_peak) if knn_tf else None, "traffic": None,
-                     "peak_source": "FFMA probe pb200_fma_peak_f32 timed in this run (MEASURED_PEAKS.json has no FP32 "
-                                    "figure)", "algorithmic": "2*Nq*Nr*d FLOP per launch x fraction of 256x128 tiles visited (exact "
-                                    "projection pruning skips the rest); 'effective' counts the skipped tiles too",
-                     "tiles_visited_frac": visited, "effective_tflops": knn_alg_tf, "ms_per_launch": knn_ms},
+        "roofline": knn_roof,
         "roofline_spmv": {"bound": "hbm", "kernel": "csr_spmv_kernel<16>", "achieved": spmv_gbs, "peak": hbm_peak,
                           "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
                           "algorithmic": "12*nnz + 4*(N+1) + 16*N bytes per launch", "ms_per_launch": spmv_ms},
@@ -319,9 +340,10 @@ def run_gpu_arm(args):
         "lanczos": utils.LAST_INFO.get("lanczos"),
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 def _quiet_stdout():

@@ -112,7 +112,7 @@ def flush_profile():
 # ---------------------------------------------------------------------------
 KNN_MAX_KEEP = 48
 # candidate-generation engine: "simt" (FP32 FFMA kernel) or "tc" (tcgen05 3xTF32 kernel, d <= 128)
-KNN_ENGINE = os.environ.get("PB200_KNN_ENGINE", "simt")
+KNN_ENGINE = os.environ.get("PB200_KNN_ENGINE", "tc")
 
 
 def sklearn_uses_brute(n: int, d: int, n_neighbors: int) -> bool:
@@ -147,6 +147,9 @@ def principal_axes(x: torch.Tensor, mean: torch.Tensor, n_axes: int = 3, iters: 
     *quality* of the pruning depends on them: any orthonormal set gives valid bounds."""
     from . import _dist
 
+    if x.shape[0] > 250_000:
+        # the axes only steer the pruning: a strided sample of ~125k rows pins them well enough
+        x = x[:: x.shape[0] // 125_000].contiguous()
     n, d = x.shape
     is64 = int(x.dtype == F64)
     n_axes = min(n_axes, d)
@@ -243,9 +246,9 @@ def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
     cand = empty((nq, k_keep), I32)
     score = empty((nq, k_keep), F32)
     thr = empty((nq,), F32)
+    use_tc = prep.xtc is not None
     lists = empty((round_up(nq, 256) * 64,), I64)
     visited = zeros((1,), I64)
-    use_tc = prep.xtc is not None
     with stage("knn_candidates"):
         if use_tc:
             call("pb200_knn_candidates_tc", prep.xtc, prep.ld, prep.yn, prep.xcn, prep.box_lo, prep.box_hi, q0, nq,

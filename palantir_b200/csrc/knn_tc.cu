@@ -35,7 +35,6 @@ constexpr int TC_KSTEP = TC_BN * 8 * 4;         // bytes of one k-step (8 coordi
 constexpr int TC_CAP = 64;
 constexpr int TC_HIGH = 56;
 constexpr int TC_MAX_KEEP = 48;
-constexpr int TC_MAX_KCH = 8;     // d_pad8 <= 128
 constexpr int TC_THREADS = 192;   // 6 warps
 
 struct TcParams {
@@ -207,8 +206,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
     unsigned long long visited = 0;
     for (;;) {
       // ---- choose the next tile (warp-collective box tests) ----
-      float bmax = fmaxf(fmaxf(ctl.warp_bound[0], ctl.warp_bound[1]), fmaxf(ctl.warp_bound[2], ctl.warp_bound[3]));
-      bmax = *(volatile float*)&ctl.warp_bound[0];
+      float bmax = *(volatile float*)&ctl.warp_bound[0];
       bmax = fmaxf(bmax, *(volatile float*)&ctl.warp_bound[1]);
       bmax = fmaxf(bmax, *(volatile float*)&ctl.warp_bound[2]);
       bmax = fmaxf(bmax, *(volatile float*)&ctl.warp_bound[3]);
@@ -281,7 +279,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       mbar_wait(&ctl.a_full, 0);
       tc_fence_after();
-      const uint32_t a_base = smem_u32(a_smem), b_base = smem_u32(b_smem);
+      const uint64_t a_desc0 = tc_smem_desc(smem_u32(a_smem)), b_desc0 = tc_smem_desc(smem_u32(b_smem));
       int tcount = 0;
       for (int g = 0;; ++g) {
         const int st = g % NST;
@@ -305,15 +303,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
           bulk_g2s(&ctl.yn[buf][0], p.yn + (long long)tile * TC_BN, TC_BN * 4, &ctl.yn_full[buf]);
         }
         const uint32_t d_tmem = tmem + (uint32_t)buf * TC_BN;
-        const int steps = (kc == KCH - 1) ? p.tail_steps : 2;
-        for (int s = 0; s < steps; ++s) {
-          const uint32_t ao = a_base + (uint32_t)kc * TC_STAGE + (uint32_t)s * TC_KSTEP;
-          const uint32_t bo = b_base + (uint32_t)st * TC_STAGE + (uint32_t)s * TC_KSTEP;
-          const uint64_t a_hi = tc_smem_desc(ao), a_lo = tc_smem_desc(ao + TC_HALF);
-          const uint64_t b_hi = tc_smem_desc(bo), b_lo = tc_smem_desc(bo + TC_HALF);
-          tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, (kc | s) != 0 ? 1u : 0u);
-          tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-          tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, 1u);
+        // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4) to a base
+        const uint64_t a_hi = a_desc0 + (uint64_t)((uint32_t)kc * (TC_STAGE >> 4));
+        const uint64_t b_hi = b_desc0 + (uint64_t)((uint32_t)st * (TC_STAGE >> 4));
+        tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, kc != 0 ? 1u : 0u);
+        tc_mma_tf32(d_tmem, a_hi, b_hi + (TC_HALF >> 4), idesc, 1u);
+        tc_mma_tf32(d_tmem, a_hi + (TC_HALF >> 4), b_hi, idesc, 1u);
+        if (kc < KCH - 1 || p.tail_steps == 2) {
+          tc_mma_tf32(d_tmem, a_hi + (TC_KSTEP >> 4), b_hi + (TC_KSTEP >> 4), idesc, 1u);
+          tc_mma_tf32(d_tmem, a_hi + (TC_KSTEP >> 4), b_hi + ((TC_KSTEP + TC_HALF) >> 4), idesc, 1u);
+          tc_mma_tf32(d_tmem, a_hi + ((TC_KSTEP + TC_HALF) >> 4), b_hi + (TC_KSTEP >> 4), idesc, 1u);
         }
         tc_commit(&ctl.b_empty[st]);               // stage reusable once these MMAs have read it
         if (kc == KCH - 1) {
@@ -342,13 +341,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         uint32_t v[32];
         tc_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + cb * 32), v);
         float thr = ctl.thr[row];
-        float m = INFINITY;
+        float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = fmaf(-2.f, __uint_as_float(v[j]), ctl.yn[buf][cb * 32 + j]);
-          v[j] = __float_as_uint(s);
-          m = fminf(m, s);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 y = *reinterpret_cast<const float4*>(&ctl.yn[buf][cb * 32 + j4 * 4]);
+          const float s0 = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 0]), y.x);
+          const float s1 = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 1]), y.y);
+          const float s2 = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 2]), y.z);
+          const float s3 = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 3]), y.w);
+          v[j4 * 4 + 0] = __float_as_uint(s0); v[j4 * 4 + 1] = __float_as_uint(s1);
+          v[j4 * 4 + 2] = __float_as_uint(s2); v[j4 * 4 + 3] = __float_as_uint(s3);
+          m0 = fminf(m0, s0); m1 = fminf(m1, s1); m2 = fminf(m2, s2); m3 = fminf(m3, s3);
         }
+        const float m = fminf(fminf(m0, m1), fminf(m2, m3));
         if (__any_sync(0xffffffffu, m < thr)) {
           unsigned int pending = 0xffffffffu;
           for (;;) {

@@ -10,9 +10,11 @@ ap.add_argument("--n", type=int, default=151552)
 ap.add_argument("--d", type=int, default=100)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--no-prune", action="store_true")
+ap.add_argument("--engine", default="simt")
 a = ap.parse_args()
 x, _ = synth_branching(a.n, a.d)
 xd = dv.to_device(x)
+dv.KNN_ENGINE = a.engine
 prep = dv.knn_prepare(xd, prune=not a.no_prune)
 for r in range(a.reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -90,6 +90,31 @@ def test_knn_matches_sklearn_live(pb, po, n, d, k, dtype):
     assert np.max(np.abs(a - b)) <= tol * max(1.0, b.max()) + (0 if tol else 0)
 
 
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+@pytest.mark.parametrize("n,d,dtype", [(3000, 100, np.float32), (1500, 20, np.float32), (2500, 128, np.float64),
+                                       (700, 17, np.float32), (5000, 50, np.float32)])
+def test_knn_both_engines_match_sklearn(pb, po, engine, n, d, dtype):
+    """FP32 SIMT kernel and tcgen05 3xTF32 kernel: identical neighbour sets, sklearn's distances."""
+    from palantir_b200 import _device as dv
+
+    rng = np.random.default_rng(n * 7 + d)
+    x = (rng.normal(size=(n, d)) * rng.uniform(0.3, 2.0, size=d) + rng.normal(size=d)).astype(dtype)
+    ref_d, ref_i = po.knn_with_self(x, 31)
+    old = dv.KNN_ENGINE
+    dv.KNN_ENGINE = engine
+    try:
+        idx, dist, stats = _knn(pb, x, 31)
+    finally:
+        dv.KNN_ENGINE = old
+    assert stats["engine"] == engine
+    assert _rows_equal_as_sets(idx, ref_i) == n
+    a, b = np.sort(dist, 1)[:, 1:], np.sort(ref_d, 1)[:, 1:]
+    if dtype == np.float32:
+        assert np.array_equal(a, b)
+    else:
+        assert np.max(np.abs(a - b) / b) <= 1e-12
+
+
 def test_knn_with_duplicate_points(pb, po):
     rng = np.random.default_rng(5)
     x = rng.normal(size=(400, 24)).astype(np.float32)
