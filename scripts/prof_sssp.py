@@ -45,6 +45,15 @@ def run(tag, mult=4.0, nsrc=None):
     return D
 dc.SSSP_MODE = "csr"; lib.pb200_sssp_set_variant(4)
 Dref = run("csr v4 (128 thr)")
+if "--one" in sys.argv:
+    sys.exit(0)
+if "--variants" in sys.argv:
+    for v in (2, 3, 5, 6, 7, 4):
+        lib.pb200_sssp_set_variant(v)
+        D = run(f"csr variant {v}")
+        print("   identical:", bool(torch.equal(D, Dref)), flush=True)
+        del D
+    sys.exit(0)
 run("csr v4 (128 thr)", nsrc=150)
 dc.SSSP_MODE = "arcrec"
 for thr in (128, 256, 512):
