@@ -79,8 +79,10 @@ int pb200_knn_rerank_f64(const void* x, int is_f64, const int* perm, const doubl
 
 /* Tensor-core (tcgen05, 3xTF32) candidate generation: same outputs as pb200_knn_candidates_f32 for d <= 128.
  * xtc: TF32 hi/lo operand copy (pb200_knn_tc_operand_floats floats) written by pb200_knn_prepare_tc; q0 % 128 == 0;
- * lists: ceil(nq/128)*128*64 64-bit words.  The re-rank certificate uses eps_coef = 2 (16 + 4 * 3 * ceil(d/8)). */
+ * lists: ceil(nq/128)*128*pb200_knn_tc_list_cap() 64-bit words.  The re-rank certificate uses
+ * eps_coef = 2 (16 + 4 * 3 * ceil(d/8)). */
 long long pb200_knn_tc_operand_floats(long long n_pad, int d);
+int pb200_knn_tc_list_cap(void);
 int pb200_knn_prepare_tc(const void* x, int is_f64, long long n, int d, long long n_pad, const double* mean,
                          const int* perm, float* xtc, void* stream);
 int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, const double* xcn,

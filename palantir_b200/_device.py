@@ -247,7 +247,8 @@ def knn_expanded(prep: KnnPrep, k: int, q0: int = 0, nq: Optional[int] = None,
     score = empty((nq, k_keep), F32)
     thr = empty((nq,), F32)
     use_tc = prep.xtc is not None
-    lists = empty((round_up(nq, 256) * 64,), I64)
+    cap = int(_native.load().pb200_knn_tc_list_cap()) if use_tc else 64
+    lists = empty((round_up(nq, 256) * cap,), I64)
     visited = zeros((1,), I64)
     with stage("knn_candidates"):
         if use_tc:

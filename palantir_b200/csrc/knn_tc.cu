@@ -9,19 +9,26 @@
 //     hi = tf32(x), lo = tf32(x - hi); the dot product is accumulated as
 //     hi.hi + hi.lo + lo.hi (the lo.lo term is below 2^-22 |x||y| and is covered by the
 //     certificate's error bound) -- three tcgen05.mma.kind::tf32 per 8 coordinates;
-//   * a CTA owns 128 query rows whose hi/lo operand stays RESIDENT in shared memory for the
-//     whole kernel; reference tiles (128 points) stream through a ring of 16-coordinate stages,
+//   * a CTA owns 128 query rows whose hi/lo operand stays RESIDENT IN TENSOR MEMORY for the whole
+//     kernel (lane = row, one column per coordinate: 2 x d8 of the 512 columns, written once with
+//     tcgen05.st) and is read from there by the MMAs -- with both operands in shared memory a
+//     128x128x8 TF32 MMA has to read 8 KB per 64 cycles, all of the SM's shared-memory bandwidth,
+//     and measured 151 cycles; reference tiles (128 points) stream through a ring of 16-coordinate stages,
 //     one bulk copy each (the global copy is stored directly in the UMMA "K-major, no swizzle"
 //     core-matrix layout: 8 rows x 16 bytes per core matrix, LBO = 2048 B between K-adjacent
 //     core matrices, SBO = 128 B between 8-row groups);
-//   * the 128 x 128 FP32 accumulator lives in TMEM, double buffered (2 x 128 columns) so that
-//     the MMAs of tile t+1 run while the four epilogue warps drain tile t with tcgen05.ld
+//   * the 128 x 128 FP32 accumulator lives in TMEM, four deep (4 x 128 columns = the whole TMEM of
+//     the SM: the epilogue's time per tile varies a lot with the number of candidates it has to
+//     keep, and the depth absorbs that) so that the MMAs of the next tiles run while the four
+//     epilogue warps drain tile t with tcgen05.ld
 //     (32 lanes x 32 columns per instruction; lane = query row, so a thread owns one row and
 //     its candidate list);
 //   * warp roles: warp 0 = producer (tile choice with 32 box tests per step + bulk copies),
 //     warp 1 = MMA issuer (one elected lane) and TMEM allocator, warps 2-5 = epilogue.
-// Supports d <= 128 (the resident operand and the ring must fit 227 KB); larger d uses the
-// SIMT kernel.
+// Supports d <= 128 (the resident operand and two accumulators must fit the 512 TMEM columns);
+// larger d uses the SIMT kernel.
+#include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace pb200 {
@@ -32,9 +39,12 @@ constexpr int TC_KC = 16;         // coordinates per ring stage (two MMA k-steps
 constexpr int TC_HALF = TC_BN * TC_KC * 4;      // bytes of one hi (or lo) block of a stage: 8 KB
 constexpr int TC_STAGE = 2 * TC_HALF;           // hi + lo: 16 KB
 constexpr int TC_KSTEP = TC_BN * 8 * 4;         // bytes of one k-step (8 coordinates) inside a block: 4 KB
-constexpr int TC_CAP = 64;
-constexpr int TC_HIGH = 56;
+constexpr int TC_CAP = 128;       // candidate buffer entries per row (shared memory)
+constexpr int TC_LSTRIDE = TC_CAP + 1;   // row stride of the buffers in 64-bit words (odd: rows start on different banks)
+constexpr int TC_HIGH = TC_CAP - 32;     // a row above this is compacted before its thread may push (<= 32 pushes per step)
+constexpr int TC_NST = 5;         // ring stages (16 KB each); the depth does not matter beyond 3 (measured)
 constexpr int TC_MAX_KEEP = 48;
+constexpr int TC_NACC = 4;        // TMEM accumulators (4 x 128 columns = all 512 columns of the SM)
 constexpr int TC_THREADS = 192;   // 6 warps
 
 struct TcParams {
@@ -47,7 +57,10 @@ struct TcParams {
   int kch;                // ring stages per tile = ceil(d_pad8 / 16)
   int tail_steps;         // k-steps in the last stage of a tile (1 or 2)
   int nst;                // ring depth
+  int d8;                 // coordinates rounded up to 8 (TMEM columns of one half of the query operand)
+  int nacc;               // TMEM accumulators in flight: (512 - 2 d8) / 128, 2..4
   int k_keep;
+  int debug;              // dev only (PB200_TC_DEBUG): 1 = epilogue releases accumulators unread, 2 = no candidate pushes
   unsigned long long* lists;
   int* out_idx;
   float* out_score;
@@ -58,15 +71,15 @@ struct TcParams {
 struct TcCtl {
   uint64_t a_full;
   uint64_t b_full[8], b_empty[8];
-  uint64_t acc_full[2], acc_empty[2];
-  uint64_t yn_full[2];
-  int meta_tile[8], meta_kc[8];
-  int acc_tile[2];
+  uint64_t acc_full[TC_NACC], acc_empty[TC_NACC];
+  uint64_t yn_full[TC_NACC];
+  int tile_ring[16];      // tile ids, producer -> MMA issuer (one entry per tile)
+  int acc_tile[TC_NACC];
   int cnt[TC_BM];
   float thr[TC_BM];
   float xcn[TC_BM];
   float warp_bound[4];
-  float yn[2][TC_BN];
+  alignas(16) float yn[TC_NACC][TC_BN];   // bulk-copy destination and float4 reads
   double qlo[3], qhi[3];
   uint32_t tmem_base;
 };
@@ -89,6 +102,35 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
       : "memory");
+}
+
+// A operand read from TMEM (lane = row, one 32-bit column per coordinate), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc,
+                                               uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_st4(uint32_t taddr, const float4& v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v.x)),
+               "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
+               : "memory");
+}
+
+// exactly one lane of a converged warp (elect.sync): lets the compiler issue the uniform-datapath
+// tcgen05 instructions without its per-active-thread ELECT loop
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -120,44 +162,75 @@ __device__ __forceinline__ int tc_tile_of(int s, int q, int T) {
   return R > L ? q + m + rest : q - 1 - m - rest;
 }
 
-// warp-collective compaction of one row's candidate buffer (see knn_f32.cu)
+// Warp-collective compaction of one row's candidate buffer: keeps the k_keep smallest of its c <= 128
+// entries (four per lane) and sets the row's threshold to the k_keep-th smallest score.  The k_keep-th
+// smallest 32-bit key is found by a bitwise search below the keys' common prefix (one warp reduction per
+// bit), then the survivors are written back by ballot-prefix positions -- no ranking: the order inside
+// the buffer is irrelevant until the final emit.
 __device__ __noinline__ void tc_compact_row(TcCtl* ctl, unsigned long long* buf, int row, int k_keep, int lane) {
   int c = ctl->cnt[row];
   c = c < TC_CAP ? c : TC_CAP;
-  const unsigned long long e0 = lane < c ? __ldcg(buf + lane) : ~0ull;
-  const unsigned long long e1 = lane + 32 < c ? __ldcg(buf + lane + 32) : ~0ull;
-  int r0 = 0, r1 = 0;
-#pragma unroll 8
-  for (int j = 0; j < 32; ++j) {
-    const unsigned long long o0 = __shfl_sync(0xffffffffu, e0, j);
-    const unsigned long long o1 = __shfl_sync(0xffffffffu, e1, j);
-    r0 += (o0 < e0) + (o1 < e0);
-    r1 += (o0 < e1) + (o1 < e1);
+  if (c <= k_keep) return;
+  unsigned long long e[4];
+  uint32_t key[4];
+  uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = lane + 32 * q;
+    e[q] = i < c ? buf[i] : ~0ull;
+    key[q] = (uint32_t)(e[q] >> 32);
+    mn = key[q] < mn ? key[q] : mn;
+    if (i < c) mx = key[q] > mx ? key[q] : mx;
   }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  uint32_t piv = mn;
+  if (mn != mx) {
+    const int hb = 31 - __clz(mn ^ mx);
+    piv = hb == 31 ? 0u : (mn & ~((2u << hb) - 1u));
+    for (int b = hb; b >= 0; --b) {
+      const uint32_t cand = piv | (1u << b);
+      const int cl = (int)(key[0] < cand) + (int)(key[1] < cand) + (int)(key[2] < cand) + (int)(key[3] < cand);
+      if ((int)__reduce_add_sync(0xffffffffu, (unsigned)cl) < k_keep) piv = cand;
+    }
+  }
+  // piv = k_keep-th smallest key: everything below it stays, ties at piv fill the remaining slots
+  const int nl = (int)(key[0] < piv) + (int)(key[1] < piv) + (int)(key[2] < piv) + (int)(key[3] < piv);
+  const int n_less = (int)__reduce_add_sync(0xffffffffu, (unsigned)nl);
+  const int allowed = k_keep - n_less;
+  const unsigned lt = (1u << lane) - 1u;
+  int base = 0, tbase = 0;
   __syncwarp();
-  if (lane < c && r0 < k_keep) __stcg(buf + r0, e0);
-  if (lane + 32 < c && r1 < k_keep) __stcg(buf + r1, e1);
-  if (c >= k_keep) {
-    if (lane < c && r0 == k_keep - 1) ctl->thr[row] = f32_from_ordered((uint32_t)(e0 >> 32));
-    if (lane + 32 < c && r1 == k_keep - 1) ctl->thr[row] = f32_from_ordered((uint32_t)(e1 >> 32));
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const bool less = key[q] < piv, tie = key[q] == piv;
+    const unsigned bl = __ballot_sync(0xffffffffu, less), bt = __ballot_sync(0xffffffffu, tie);
+    if (less) buf[base + __popc(bl & lt)] = e[q];
+    if (tie) {
+      const int tp = tbase + __popc(bt & lt);
+      if (tp < allowed) buf[n_less + tp] = e[q];
+    }
+    base += __popc(bl);
+    tbase += __popc(bt);
   }
-  if (lane == 0) ctl->cnt[row] = c < k_keep ? c : k_keep;
-  __threadfence_block();
+  if (lane == 0) {
+    ctl->thr[row] = f32_from_ordered(piv);
+    ctl->cnt[row] = k_keep;
+  }
   __syncwarp();
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // [A resident: kch stages][B ring: nst stages][control]
-  unsigned char* a_smem = smem_raw;
-  unsigned char* b_smem = smem_raw + (size_t)p.kch * TC_STAGE;
-  TcCtl& ctl = *reinterpret_cast<TcCtl*>(b_smem + (size_t)p.nst * TC_STAGE);
+  // [B ring: nst stages][candidate buffers 128 x TC_LSTRIDE words][control]; the query operand lives in TMEM
+  unsigned char* b_smem = smem_raw;
+  unsigned long long* lists = reinterpret_cast<unsigned long long*>(b_smem + (size_t)p.nst * TC_STAGE);
+  TcCtl& ctl = *reinterpret_cast<TcCtl*>(lists + TC_BM * TC_LSTRIDE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qbase = p.q0 + blockIdx.x * TC_BM;
   const int row_local0 = blockIdx.x * TC_BM;
   const int qtile = qbase / TC_BN;
   const int KCH = p.kch, NST = p.nst, T = p.n_tiles;
-  unsigned long long* lists = p.lists + (long long)row_local0 * TC_CAP;
 
   for (int r = tid; r < TC_BM; r += TC_THREADS) {
     ctl.cnt[r] = 0;
@@ -166,17 +239,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
   }
   if (tid < 4) ctl.warp_bound[tid] = (row_local0 + tid * 32 < p.nq) ? INFINITY : -INFINITY;
   if (tid == 0) {
-    mbar_init(&ctl.a_full, 1);
+    mbar_init(&ctl.a_full, 4);
     for (int s = 0; s < NST; ++s) { mbar_init(&ctl.b_full[s], 1); mbar_init(&ctl.b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&ctl.acc_full[b], 1); mbar_init(&ctl.acc_empty[b], 4); mbar_init(&ctl.yn_full[b], 1); }
+    for (int b = 0; b < TC_NACC; ++b) { mbar_init(&ctl.acc_full[b], 1); mbar_init(&ctl.acc_empty[b], 4); mbar_init(&ctl.yn_full[b], 1); }
     fence_mbar_init();
     if (p.box_lo) {
       for (int a = 0; a < 3; ++a) { ctl.qlo[a] = p.box_lo[(long long)qtile * 3 + a]; ctl.qhi[a] = p.box_hi[(long long)qtile * 3 + a]; }
     }
   }
   if (warp == 1) {
-    // TMEM: 2 accumulators x 128 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl.tmem_base)), "r"(256));
+    // TMEM, all 512 columns: nacc accumulators x 128 columns, then the query operand (hi | lo, d8 columns each)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl.tmem_base)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
@@ -184,82 +257,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
   tc_fence_after();
   const uint32_t tmem = ctl.tmem_base;
   const uint32_t last_bytes = (uint32_t)p.tail_steps * TC_KSTEP;   // bytes of a hi (or lo) block in the last stage
+  const int NACC = p.nacc;
+  const uint32_t acol_hi = (uint32_t)(NACC * TC_BN), acol_lo = acol_hi + (uint32_t)p.d8;
 
   if (warp == 0) {
     // ================= producer =================
-    if (lane == 0) {
-      // resident query operand
-      uint32_t tx = 0;
-      for (int kc = 0; kc < KCH; ++kc) tx += (kc == KCH - 1) ? 2 * last_bytes : (uint32_t)TC_STAGE;
-      mbar_arrive_expect_tx(&ctl.a_full, tx);
-      for (int kc = 0; kc < KCH; ++kc) {
-        const float* src = p.xtc + ((long long)qtile * KCH + kc) * (TC_STAGE / 4);
-        if (kc < KCH - 1 || p.tail_steps == 2) {
-          bulk_g2s(a_smem + (size_t)kc * TC_STAGE, src, TC_STAGE, &ctl.a_full);
-        } else {
-          bulk_g2s(a_smem + (size_t)kc * TC_STAGE, src, last_bytes, &ctl.a_full);
-          bulk_g2s(a_smem + (size_t)kc * TC_STAGE + TC_HALF, src + TC_HALF / 4, last_bytes, &ctl.a_full);
+    int cursor = 0, st = 0, tslot = 0;     // st / ph (ring slot and pass parity) live in lane 0
+    uint32_t ph = 0;
+    unsigned long long visited = 0;
+    // Tile choice, 32 candidates of the outward sequence per step (one per lane): the squared gap between
+    // the candidate's projection box and the query tile's is computed one step AHEAD (its six global loads
+    // are in flight while the previous step's tiles are being copied) and compared with the pruning bound
+    // only when the step is consumed; all accepted tiles of a step are kept in a mask and popped one by one.
+    auto gap2_of = [&](int sidx) -> double {
+      if (sidx >= T) return INFINITY;
+      if (!p.box_lo) return 0.0;
+      const int tile = tc_tile_of(sidx, qtile, T);
+      double g2 = 0.0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const double d1 = __ldg(p.box_lo + (long long)tile * 3 + a) - ctl.qhi[a];
+        const double d2 = ctl.qlo[a] - __ldg(p.box_hi + (long long)tile * 3 + a);
+        double gp = d1 > d2 ? d1 : d2;
+        gp = gp > 0.0 ? gp : 0.0;
+        g2 = fma(gp, gp, g2);
+      }
+      return g2 * (1.0 - 1e-9);
+    };
+    double g2_next = gap2_of(lane);
+    unsigned mask = 0;
+    int mask_base = 0;
+    for (;;) {
+      // ---- choose the next tile ----
+      int chosen = -1;
+      if (mask == 0) {
+        float bmax = *(volatile float*)&ctl.warp_bound[0];
+        bmax = fmaxf(bmax, *(volatile float*)&ctl.warp_bound[1]);
+        bmax = fmaxf(bmax, *(volatile float*)&ctl.warp_bound[2]);
+        bmax = fmaxf(bmax, *(volatile float*)&ctl.warp_bound[3]);
+        const double bound = (double)bmax;
+        while (cursor < T) {
+          const double g2 = g2_next;
+          mask_base = cursor;
+          cursor += 32;
+          g2_next = gap2_of(cursor + lane);
+          mask = __ballot_sync(0xffffffffu, !(g2 > bound));     // candidates past the end are masked off below
+          if (mask_base + 32 > T) mask &= (1u << (T - mask_base)) - 1u;
+          if (mask) break;
         }
       }
-    }
-    int cursor = 0, g = 0;
-    unsigned long long visited = 0;
-    for (;;) {
-      // ---- choose the next tile (warp-collective box tests) ----
-      float bmax = *(volatile float*)&ctl.warp_bound[0];
-      bmax = fmaxf(bmax, *(volatile float*)&ctl.warp_bound[1]);
-      bmax = fmaxf(bmax, *(volatile float*)&ctl.warp_bound[2]);
-      bmax = fmaxf(bmax, *(volatile float*)&ctl.warp_bound[3]);
-      const double bound = (double)bmax;
-      int chosen = -1;
-      while (cursor < T) {
-        const int sidx = cursor + lane;
-        const int tile = sidx < T ? tc_tile_of(sidx, qtile, T) : -1;
-        bool ok = false;
-        if (tile >= 0) {
-          if (!p.box_lo) ok = true;
-          else {
-            double g2 = 0.0;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-              const double d1 = p.box_lo[(long long)tile * 3 + a] - ctl.qhi[a];
-              const double d2 = ctl.qlo[a] - p.box_hi[(long long)tile * 3 + a];
-              double gp = d1 > d2 ? d1 : d2;
-              gp = gp > 0.0 ? gp : 0.0;
-              g2 = fma(gp, gp, g2);
-            }
-            ok = !(g2 * (1.0 - 1e-9) > bound);
-          }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        if (m) {
-          const int first = __ffs(m) - 1;
-          chosen = __shfl_sync(0xffffffffu, tile, first);
-          cursor += first + 1;
-          break;
-        }
-        cursor += 32;
+      if (mask) {
+        const int bit = __ffs(mask) - 1;
+        mask &= mask - 1;
+        chosen = tc_tile_of(mask_base + bit, qtile, T);
       }
       if (chosen < 0) {
         // end of stream
-        const int st = g % NST;
         if (lane == 0) {
-          mbar_wait(&ctl.b_empty[st], (((uint32_t)(g / NST)) & 1u) ^ 1u);
-          ctl.meta_tile[st] = -1;
+          mbar_wait(&ctl.b_empty[st], ph ^ 1u);
+          ctl.tile_ring[tslot] = -1;
           mbar_arrive(&ctl.b_full[st]);
         }
         break;
       }
       ++visited;
       if (lane == 0) {
-        for (int kc = 0; kc < KCH; ++kc, ++g) {
-          const int st = g % NST;
-          mbar_wait(&ctl.b_empty[st], (((uint32_t)(g / NST)) & 1u) ^ 1u);
-          ctl.meta_tile[st] = chosen;
-          ctl.meta_kc[st] = kc;
-          const float* src = p.xtc + ((long long)chosen * KCH + kc) * (TC_STAGE / 4);
+        ctl.tile_ring[tslot] = chosen;           // published by the release of the first stage's arrive
+        const float* src = p.xtc + (long long)chosen * KCH * (TC_STAGE / 4);
+        for (int kc = 0; kc < KCH; ++kc) {
+          mbar_wait(&ctl.b_empty[st], ph ^ 1u);
           unsigned char* dst = b_smem + (size_t)st * TC_STAGE;
-          if (kc < KCH - 1 || p.tail_steps == 2) {
+          if ((p.debug & 7) == 4) {
+            mbar_arrive(&ctl.b_full[st]);          // dev: no copy, the MMAs read whatever is in the ring
+          } else if (kc < KCH - 1 || p.tail_steps == 2) {
             mbar_arrive_expect_tx(&ctl.b_full[st], TC_STAGE);
             bulk_g2s(dst, src, TC_STAGE, &ctl.b_full[st]);
           } else {
@@ -267,81 +337,158 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
             bulk_g2s(dst, src, last_bytes, &ctl.b_full[st]);
             bulk_g2s(dst + TC_HALF, src + TC_HALF / 4, last_bytes, &ctl.b_full[st]);
           }
+          src += TC_STAGE / 4;
+          if (++st == NST) { st = 0; ph ^= 1u; }
         }
       }
-      g = __shfl_sync(0xffffffffu, g, 0);
+      tslot = (tslot + 1) & 15;
     }
     if (lane == 0 && p.tiles_visited) atomicAdd(p.tiles_visited, visited);
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (tc_elect_one()) {
       // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      mbar_wait(&ctl.a_full, 0);
+      mbar_wait(&ctl.a_full, 0);                 // query operand stored to TMEM by the epilogue warps
       tc_fence_after();
-      const uint64_t a_desc0 = tc_smem_desc(smem_u32(a_smem)), b_desc0 = tc_smem_desc(smem_u32(b_smem));
-      int tcount = 0;
-      for (int g = 0;; ++g) {
-        const int st = g % NST;
-        mbar_wait(&ctl.b_full[st], ((uint32_t)(g / NST)) & 1u);
+      const uint64_t b_desc0 = tc_smem_desc(smem_u32(b_smem));
+      int st = 0, tslot = 0, buf = 0;
+      uint32_t ph = 0, accph = 0;
+      long long t_wait_b = 0, t_wait_acc = 0, t_mma = 0, t_commit = 0, t_tiles = 0;   // dev timers (debug & 8)
+      const bool timing = (p.debug & 8) != 0;
+      long long t_each[6] = {0, 0, 0, 0, 0, 0};
+      const long long t_begin = clock64();
+      for (;;) {
+        // ---- one reference tile: KCH ring stages into accumulator `buf` ----
+        long long c0 = timing ? clock64() : 0;
+        mbar_wait(&ctl.b_full[st], ph);
+        if (timing) { const long long c1 = clock64(); t_wait_b += c1 - c0; c0 = c1; }
+        const int tile = ctl.tile_ring[tslot];
+        tslot = (tslot + 1) & 15;
+        mbar_wait(&ctl.acc_empty[buf], accph ^ 1u);
         tc_fence_after();
-        const int tile = ctl.meta_tile[st];
-        const int buf = tcount & 1;
+        if (timing) { const long long c1 = clock64(); t_wait_acc += c1 - c0; c0 = c1; }
         if (tile < 0) {
           // end of stream: tell the epilogue (no MMA pending on this buffer: plain arrive)
-          mbar_wait(&ctl.acc_empty[buf], (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);
           ctl.acc_tile[buf] = -1;
           mbar_arrive(&ctl.acc_full[buf]);
+          if (timing && blockIdx.x == 0)
+            printf("tc mma thread: tiles %lld total %lld cyc; per tile: wait_b %lld wait_acc %lld mma %lld commit %lld\n", t_tiles,
+                   clock64() - t_begin, t_wait_b / (t_tiles + 1), t_wait_acc / (t_tiles + 1), t_mma / (t_tiles + 1),
+                   t_commit / (t_tiles + 1));
+          if (timing && blockIdx.x == 0 && (p.debug & 16))
+            printf("   per tile, issue of each of the six MMAs of a stage: %lld %lld %lld %lld %lld %lld\n", t_each[0] / (t_tiles + 1),
+                   t_each[1] / (t_tiles + 1), t_each[2] / (t_tiles + 1), t_each[3] / (t_tiles + 1), t_each[4] / (t_tiles + 1),
+                   t_each[5] / (t_tiles + 1));
           break;
         }
-        const int kc = ctl.meta_kc[st];
-        if (kc == 0) {
-          mbar_wait(&ctl.acc_empty[buf], (((uint32_t)(tcount >> 1)) & 1u) ^ 1u);
-          tc_fence_after();
-          // reference norms of this tile for the epilogue
-          mbar_arrive_expect_tx(&ctl.yn_full[buf], TC_BN * 4);
-          bulk_g2s(&ctl.yn[buf][0], p.yn + (long long)tile * TC_BN, TC_BN * 4, &ctl.yn_full[buf]);
-        }
+        ++t_tiles;
+        // reference norms of this tile for the epilogue
+        mbar_arrive_expect_tx(&ctl.yn_full[buf], TC_BN * 4);
+        bulk_g2s(&ctl.yn[buf][0], p.yn + (long long)tile * TC_BN, TC_BN * 4, &ctl.yn_full[buf]);
         const uint32_t d_tmem = tmem + (uint32_t)buf * TC_BN;
-        // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4) to a base
-        const uint64_t a_hi = a_desc0 + (uint64_t)((uint32_t)kc * (TC_STAGE >> 4));
-        const uint64_t b_hi = b_desc0 + (uint64_t)((uint32_t)st * (TC_STAGE >> 4));
-        tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, kc != 0 ? 1u : 0u);
-        tc_mma_tf32(d_tmem, a_hi, b_hi + (TC_HALF >> 4), idesc, 1u);
-        tc_mma_tf32(d_tmem, a_hi + (TC_HALF >> 4), b_hi, idesc, 1u);
-        if (kc < KCH - 1 || p.tail_steps == 2) {
-          tc_mma_tf32(d_tmem, a_hi + (TC_KSTEP >> 4), b_hi + (TC_KSTEP >> 4), idesc, 1u);
-          tc_mma_tf32(d_tmem, a_hi + (TC_KSTEP >> 4), b_hi + ((TC_KSTEP + TC_HALF) >> 4), idesc, 1u);
-          tc_mma_tf32(d_tmem, a_hi + ((TC_KSTEP + TC_HALF) >> 4), b_hi + (TC_KSTEP >> 4), idesc, 1u);
+        uint32_t a_hi = tmem + acol_hi, a_lo = tmem + acol_lo;
+        for (int kc = 0; kc < KCH; ++kc) {
+          if (kc > 0) {
+            if (timing) c0 = clock64();
+            mbar_wait(&ctl.b_full[st], ph);
+            tc_fence_after();
+            if (timing) { const long long c1 = clock64(); t_wait_b += c1 - c0; c0 = c1; }
+          }
+          // three products per k-step: hi.hi + hi.lo + lo.hi; B descriptors differ only in the start-address field
+          const uint64_t b_hi = b_desc0 + (uint64_t)((uint32_t)st * (TC_STAGE >> 4));
+          if (timing && (p.debug & 16)) {
+            // dev: per-instruction issue times of a full stage
+            long long q0 = clock64(), q1;
+            tc_mma_tf32_ts(d_tmem, a_hi, b_hi, idesc, kc != 0 ? 1u : 0u);
+            q1 = clock64(); t_each[0] += q1 - q0; q0 = q1;
+            tc_mma_tf32_ts(d_tmem, a_hi, b_hi + (TC_HALF >> 4), idesc, 1u);
+            q1 = clock64(); t_each[1] += q1 - q0; q0 = q1;
+            tc_mma_tf32_ts(d_tmem, a_lo, b_hi, idesc, 1u);
+            q1 = clock64(); t_each[2] += q1 - q0; q0 = q1;
+            if (kc < KCH - 1 || p.tail_steps == 2) {
+              tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
+              q1 = clock64(); t_each[3] += q1 - q0; q0 = q1;
+              tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + ((TC_KSTEP + TC_HALF) >> 4), idesc, 1u);
+              q1 = clock64(); t_each[4] += q1 - q0; q0 = q1;
+              tc_mma_tf32_ts(d_tmem, a_lo + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
+              q1 = clock64(); t_each[5] += q1 - q0; q0 = q1;
+            }
+          } else {
+          tc_mma_tf32_ts(d_tmem, a_hi, b_hi, idesc, kc != 0 ? 1u : 0u);
+            if ((p.debug & 7) != 3) {
+              tc_mma_tf32_ts(d_tmem, a_hi, b_hi + (TC_HALF >> 4), idesc, 1u);
+              tc_mma_tf32_ts(d_tmem, a_lo, b_hi, idesc, 1u);
+            }
+            if (kc < KCH - 1 || p.tail_steps == 2) {
+              tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
+              if ((p.debug & 7) != 3) {
+                tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + ((TC_KSTEP + TC_HALF) >> 4), idesc, 1u);
+                tc_mma_tf32_ts(d_tmem, a_lo + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
+              }
+            }
+          }
+          if (timing) { const long long c1 = clock64(); t_mma += c1 - c0; c0 = c1; }
+          tc_commit(&ctl.b_empty[st]);               // stage reusable once these MMAs have read it
+          if (timing) { const long long c1 = clock64(); t_commit += c1 - c0; c0 = c1; }
+          a_hi += TC_KC; a_lo += TC_KC;
+          if (++st == NST) { st = 0; ph ^= 1u; }
         }
-        tc_commit(&ctl.b_empty[st]);               // stage reusable once these MMAs have read it
-        if (kc == KCH - 1) {
-          ctl.acc_tile[buf] = tile;
-          tc_commit(&ctl.acc_full[buf]);           // accumulator complete
-          ++tcount;
-        }
+        ctl.acc_tile[buf] = tile;
+        tc_commit(&ctl.acc_full[buf]);               // accumulator complete
+        if (++buf == NACC) { buf = 0; accph ^= 1u; }
       }
     }
   } else {
     // ================= epilogue (warps 2..5): TMEM lane quarter = warp % 4 =================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;           // CTA-local query row owned by this thread
-    unsigned long long* mybuf = lists + (long long)row * TC_CAP;
+    unsigned long long* mybuf = lists + row * TC_LSTRIDE;
     bool compacted_any = false;
-    for (int t = 0;; ++t) {
-      const int buf = t & 1;
-      mbar_wait(&ctl.acc_full[buf], ((uint32_t)(t >> 1)) & 1u);
+    {
+      // this thread's query row -> TMEM lane `row`: hi coordinates at columns acol_hi.., lo at acol_lo..
+      const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
+      const float* rowp = p.xtc + (long long)qtile * KCH * (TC_STAGE / 4) + (row >> 3) * 32 + (row & 7) * 4;
+      for (int kc = 0; kc < KCH; ++kc) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = kc * TC_KC + kk * 4;
+          if (k < p.d8) {
+            const float* src = rowp + (long long)kc * (TC_STAGE / 4) + kk * 512;
+            const float4 vh = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 vl = __ldg(reinterpret_cast<const float4*>(src + TC_HALF / 4));
+            tc_st4(lane_addr + acol_hi + (uint32_t)k, vh);
+            tc_st4(lane_addr + acol_lo + (uint32_t)k, vl);
+          }
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl.a_full);
+    }
+    int buf = -1;
+    uint32_t accph = 1;
+    for (;;) {
+      if (++buf == NACC || buf == 0) { buf = 0; accph ^= 1u; }
+      mbar_wait(&ctl.acc_full[buf], accph);
       tc_fence_after();
       const int tile = ctl.acc_tile[buf];
       if (tile < 0) break;
-      mbar_wait(&ctl.yn_full[buf], ((uint32_t)(t >> 1)) & 1u);
+      mbar_wait(&ctl.yn_full[buf], accph);
       const int colbase = tile * TC_BN;
+      if ((p.debug & 7) == 1 || (p.debug & 7) >= 3) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl.acc_empty[buf]);
+        continue;
+      }
 #pragma unroll 1
       for (int cb = 0; cb < 4; ++cb) {
         uint32_t v[32];
         tc_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + cb * 32), v);
         float thr = ctl.thr[row];
-        float m0 = INFINITY, m1 = INFINITY, m2 = INFINITY, m3 = INFINITY;
+        float q[8];                                  // minimum of each group of four columns
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 y = *reinterpret_cast<const float4*>(&ctl.yn[buf][cb * 32 + j4 * 4]);
@@ -351,39 +498,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
           const float s3 = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 3]), y.w);
           v[j4 * 4 + 0] = __float_as_uint(s0); v[j4 * 4 + 1] = __float_as_uint(s1);
           v[j4 * 4 + 2] = __float_as_uint(s2); v[j4 * 4 + 3] = __float_as_uint(s3);
-          m0 = fminf(m0, s0); m1 = fminf(m1, s1); m2 = fminf(m2, s2); m3 = fminf(m3, s3);
+          q[j4] = fminf(fminf(s0, s1), fminf(s2, s3));
         }
-        const float m = fminf(fminf(m0, m1), fminf(m2, m3));
-        if (__any_sync(0xffffffffu, m < thr)) {
-          unsigned int pending = 0xffffffffu;
-          for (;;) {
+        const float m = fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])), fminf(fminf(q[4], q[5]), fminf(q[6], q[7])));
+        if (__any_sync(0xffffffffu, m < thr) && (p.debug & 7) != 2) {
+          // room for this step's (at most 32) pushes: rows above TC_HIGH are compacted first
+          int c = ctl.cnt[row];
+          const unsigned need = __ballot_sync(0xffffffffu, c > TC_HIGH);
+          if (need) {
+            __syncwarp();
+            for (unsigned mm = need; mm; mm &= mm - 1) {
+              const int l = __ffs(mm) - 1;
+              tc_compact_row(&ctl, lists + (quarter * 32 + l) * TC_LSTRIDE, quarter * 32 + l, p.k_keep, lane);
+            }
+            compacted_any = true;
             thr = ctl.thr[row];
-            int c = ctl.cnt[row];
-            bool fail = false;
+            c = ctl.cnt[row];
+          }
+          // groups of four columns holding a candidate for any row of the warp; only those are scanned
+          unsigned hit = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = __uint_as_float(v[j]);
-              if ((pending >> j & 1u) && s < thr) {
-                if (c < TC_CAP) {
-                  __stcg(mybuf + c, tc_pack(s, colbase + cb * 32 + j));
+          for (int j4 = 0; j4 < 8; ++j4) hit |= (q[j4] < thr ? 1u : 0u) << j4;
+          const unsigned any_hit = __reduce_or_sync(0xffffffffu, hit);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            if (any_hit >> j4 & 1u) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float sc = __uint_as_float(v[j4 * 4 + i]);
+                if (sc < thr) {
+                  mybuf[c] = tc_pack(sc, colbase + cb * 32 + j4 * 4 + i);
                   ++c;
-                  pending &= ~(1u << j);
-                } else {
-                  fail = true;
                 }
               }
             }
-            ctl.cnt[row] = c;
-            __threadfence_block();
-            __syncwarp();
-            const unsigned need = __ballot_sync(0xffffffffu, c >= TC_HIGH);
-            for (unsigned mm = need; mm; mm &= mm - 1) {
-              const int l = __ffs(mm) - 1;
-              tc_compact_row(&ctl, lists + (long long)(quarter * 32 + l) * TC_CAP, quarter * 32 + l, p.k_keep, lane);
-              compacted_any = true;
-            }
-            if (!__any_sync(0xffffffffu, fail)) break;
           }
+          ctl.cnt[row] = c;
         }
       }
       tc_fence_before();
@@ -398,15 +548,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       }
     }
     // ---- emit: final sort of each row of this warp ----
+    __syncwarp();
     for (int l = 0; l < 32; ++l) {
       const int r = quarter * 32 + l;
       const int grow = row_local0 + r;
       if (grow >= p.nq) continue;
+      tc_compact_row(&ctl, lists + r * TC_LSTRIDE, r, p.k_keep, lane);   // leaves <= k_keep <= 48 entries
       int c = ctl.cnt[r];
-      c = c < TC_CAP ? c : TC_CAP;
-      const unsigned long long* buf = lists + (long long)r * TC_CAP;
-      const unsigned long long e0 = lane < c ? __ldcg(buf + lane) : ~0ull;
-      const unsigned long long e1 = lane + 32 < c ? __ldcg(buf + lane + 32) : ~0ull;
+      c = c < 64 ? c : 64;
+      const unsigned long long* buf = lists + r * TC_LSTRIDE;
+      const unsigned long long e0 = lane < c ? buf[lane] : ~0ull;
+      const unsigned long long e1 = lane + 32 < c ? buf[lane + 32] : ~0ull;
       int q0r = 0, q1r = 0;
 #pragma unroll 8
       for (int j = 0; j < 32; ++j) {
@@ -436,7 +588,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
 }
 
@@ -503,7 +655,11 @@ int pb200_knn_prepare_tc(const void* x, int is_f64, long long n, int d, long lon
   return 0;
 }
 
-// Tensor-core version of pb200_knn_candidates_f32 (same outputs; q0 % 128 == 0; lists: ceil(nq/128)*128*64 words).
+// Entries per row of the candidate scratch passed to pb200_knn_candidates_tc.
+int pb200_knn_tc_list_cap(void) { return 1; }   // candidate buffers live in shared memory; `lists` is not used
+
+// Tensor-core version of pb200_knn_candidates_f32 (same outputs; q0 % 128 == 0; lists:
+// ceil(nq/128)*128*pb200_knn_tc_list_cap() words).
 int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, const double* xcn,
                             const double* box_lo, const double* box_hi, int q0, int nq, int d, int k_keep,
                             unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
@@ -522,12 +678,18 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   p.tail_steps = (d8 % 16 == 8) ? 1 : 2;
   p.k_keep = k_keep; p.lists = lists; p.out_idx = out_idx; p.out_score = out_score; p.out_thr = out_thr;
   p.tiles_visited = tiles_visited;
-  const int avail = 227 * 1024 - (int)sizeof(TcCtl) - 1024 - p.kch * TC_STAGE;
-  int nst = avail / TC_STAGE;
-  if (nst > 8) nst = 8;
-  if (nst < 2) { set_error_msg("pb200_knn_candidates_tc: not enough shared memory for the ring"); return -1; }
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("PB200_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
+  p.d8 = d8;
+  p.nacc = (512 - 2 * d8) / TC_BN;
+  if (p.nacc > TC_NACC) p.nacc = TC_NACC;
+  int nst = TC_NST;
+  { const char* e = getenv("PB200_TC_NST"); if (e && atoi(e) >= 2 && atoi(e) < nst) nst = atoi(e); }
   p.nst = nst;
-  const int smem = (p.kch + nst) * TC_STAGE + (int)sizeof(TcCtl) + 64;
+  const int smem = nst * TC_STAGE + TC_BM * TC_LSTRIDE * 8 + (int)sizeof(TcCtl) + 64;
   PB_CHECK(cudaFuncSetAttribute(knn_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   knn_candidates_tc_kernel<<<div_up(nq, TC_BM), TC_THREADS, smem, st>>>(p);
   PB_CHECK_LAUNCH("knn_candidates_tc_kernel");
