@@ -27,7 +27,6 @@
 //     warp 1 = MMA issuer (one elected lane) and TMEM allocator, warps 2-5 = epilogue.
 // Supports d <= 128 (the resident operand and two accumulators must fit the 512 TMEM columns);
 // larger d uses the SIMT kernel.
-#include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
 
@@ -42,6 +41,7 @@ constexpr int TC_KSTEP = TC_BN * 8 * 4;         // bytes of one k-step (8 coordi
 constexpr int TC_CAP = 128;       // candidate buffer entries per row (shared memory)
 constexpr int TC_LSTRIDE = TC_CAP + 1;   // row stride of the buffers in 64-bit words (odd: rows start on different banks)
 constexpr int TC_HIGH = TC_CAP - 32;     // a row above this is compacted before its thread may push (<= 32 pushes per step)
+constexpr int TC_IDLE_MARGIN = 20;       // rows with more than k_keep + this many entries are compacted in idle time
 constexpr int TC_NST = 5;         // ring stages (16 KB each); the depth does not matter beyond 3 (measured)
 constexpr int TC_MAX_KEEP = 48;
 constexpr int TC_NACC = 4;        // TMEM accumulators (4 x 128 columns = all 512 columns of the SM)
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
     uint32_t ph = 0;
     unsigned long long visited = 0;
     // Tile choice, 32 candidates of the outward sequence per step (one per lane): the squared gap between
-    // the candidate's projection box and the query tile's is computed one step AHEAD (its six global loads
+    // the candidate's projection box and the query tile's is computed two steps AHEAD (its six global loads
     // are in flight while the previous step's tiles are being copied) and compared with the pruning bound
     // only when the step is consumed; all accepted tiles of a step are kept in a mask and popped one by one.
     auto gap2_of = [&](int sidx) -> double {
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       }
       return g2 * (1.0 - 1e-9);
     };
-    double g2_next = gap2_of(lane);
+    double g2_next = gap2_of(lane), g2_next2 = gap2_of(32 + lane);
     unsigned mask = 0;
     int mask_base = 0;
     for (;;) {
@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
           const double g2 = g2_next;
           mask_base = cursor;
           cursor += 32;
-          g2_next = gap2_of(cursor + lane);
+          g2_next = g2_next2;
+          g2_next2 = gap2_of(cursor + 32 + lane);
           mask = __ballot_sync(0xffffffffu, !(g2 > bound));     // candidates past the end are masked off below
           if (mask_base + 32 > T) mask &= (1u << (T - mask_base)) - 1u;
           if (mask) break;
@@ -327,9 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         for (int kc = 0; kc < KCH; ++kc) {
           mbar_wait(&ctl.b_empty[st], ph ^ 1u);
           unsigned char* dst = b_smem + (size_t)st * TC_STAGE;
-          if ((p.debug & 7) == 4) {
-            mbar_arrive(&ctl.b_full[st]);          // dev: no copy, the MMAs read whatever is in the ring
-          } else if (kc < KCH - 1 || p.tail_steps == 2) {
+          if (kc < KCH - 1 || p.tail_steps == 2) {
             mbar_arrive_expect_tx(&ctl.b_full[st], TC_STAGE);
             bulk_g2s(dst, src, TC_STAGE, &ctl.b_full[st]);
           } else {
@@ -354,35 +353,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       const uint64_t b_desc0 = tc_smem_desc(smem_u32(b_smem));
       int st = 0, tslot = 0, buf = 0;
       uint32_t ph = 0, accph = 0;
-      long long t_wait_b = 0, t_wait_acc = 0, t_mma = 0, t_commit = 0, t_tiles = 0;   // dev timers (debug & 8)
-      const bool timing = (p.debug & 8) != 0;
-      long long t_each[6] = {0, 0, 0, 0, 0, 0};
-      const long long t_begin = clock64();
       for (;;) {
         // ---- one reference tile: KCH ring stages into accumulator `buf` ----
-        long long c0 = timing ? clock64() : 0;
         mbar_wait(&ctl.b_full[st], ph);
-        if (timing) { const long long c1 = clock64(); t_wait_b += c1 - c0; c0 = c1; }
         const int tile = ctl.tile_ring[tslot];
         tslot = (tslot + 1) & 15;
         mbar_wait(&ctl.acc_empty[buf], accph ^ 1u);
         tc_fence_after();
-        if (timing) { const long long c1 = clock64(); t_wait_acc += c1 - c0; c0 = c1; }
         if (tile < 0) {
           // end of stream: tell the epilogue (no MMA pending on this buffer: plain arrive)
           ctl.acc_tile[buf] = -1;
           mbar_arrive(&ctl.acc_full[buf]);
-          if (timing && blockIdx.x == 0)
-            printf("tc mma thread: tiles %lld total %lld cyc; per tile: wait_b %lld wait_acc %lld mma %lld commit %lld\n", t_tiles,
-                   clock64() - t_begin, t_wait_b / (t_tiles + 1), t_wait_acc / (t_tiles + 1), t_mma / (t_tiles + 1),
-                   t_commit / (t_tiles + 1));
-          if (timing && blockIdx.x == 0 && (p.debug & 16))
-            printf("   per tile, issue of each of the six MMAs of a stage: %lld %lld %lld %lld %lld %lld\n", t_each[0] / (t_tiles + 1),
-                   t_each[1] / (t_tiles + 1), t_each[2] / (t_tiles + 1), t_each[3] / (t_tiles + 1), t_each[4] / (t_tiles + 1),
-                   t_each[5] / (t_tiles + 1));
           break;
         }
-        ++t_tiles;
         // reference norms of this tile for the epilogue
         mbar_arrive_expect_tx(&ctl.yn_full[buf], TC_BN * 4);
         bulk_g2s(&ctl.yn[buf][0], p.yn + (long long)tile * TC_BN, TC_BN * 4, &ctl.yn_full[buf]);
@@ -390,47 +373,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         uint32_t a_hi = tmem + acol_hi, a_lo = tmem + acol_lo;
         for (int kc = 0; kc < KCH; ++kc) {
           if (kc > 0) {
-            if (timing) c0 = clock64();
             mbar_wait(&ctl.b_full[st], ph);
             tc_fence_after();
-            if (timing) { const long long c1 = clock64(); t_wait_b += c1 - c0; c0 = c1; }
           }
           // three products per k-step: hi.hi + hi.lo + lo.hi; B descriptors differ only in the start-address field
           const uint64_t b_hi = b_desc0 + (uint64_t)((uint32_t)st * (TC_STAGE >> 4));
-          if (timing && (p.debug & 16)) {
-            // dev: per-instruction issue times of a full stage
-            long long q0 = clock64(), q1;
-            tc_mma_tf32_ts(d_tmem, a_hi, b_hi, idesc, kc != 0 ? 1u : 0u);
-            q1 = clock64(); t_each[0] += q1 - q0; q0 = q1;
-            tc_mma_tf32_ts(d_tmem, a_hi, b_hi + (TC_HALF >> 4), idesc, 1u);
-            q1 = clock64(); t_each[1] += q1 - q0; q0 = q1;
-            tc_mma_tf32_ts(d_tmem, a_lo, b_hi, idesc, 1u);
-            q1 = clock64(); t_each[2] += q1 - q0; q0 = q1;
-            if (kc < KCH - 1 || p.tail_steps == 2) {
-              tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
-              q1 = clock64(); t_each[3] += q1 - q0; q0 = q1;
-              tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + ((TC_KSTEP + TC_HALF) >> 4), idesc, 1u);
-              q1 = clock64(); t_each[4] += q1 - q0; q0 = q1;
-              tc_mma_tf32_ts(d_tmem, a_lo + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
-              q1 = clock64(); t_each[5] += q1 - q0; q0 = q1;
-            }
-          } else {
           tc_mma_tf32_ts(d_tmem, a_hi, b_hi, idesc, kc != 0 ? 1u : 0u);
-            if ((p.debug & 7) != 3) {
-              tc_mma_tf32_ts(d_tmem, a_hi, b_hi + (TC_HALF >> 4), idesc, 1u);
-              tc_mma_tf32_ts(d_tmem, a_lo, b_hi, idesc, 1u);
-            }
-            if (kc < KCH - 1 || p.tail_steps == 2) {
-              tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
-              if ((p.debug & 7) != 3) {
-                tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + ((TC_KSTEP + TC_HALF) >> 4), idesc, 1u);
-                tc_mma_tf32_ts(d_tmem, a_lo + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
-              }
-            }
+          tc_mma_tf32_ts(d_tmem, a_hi, b_hi + (TC_HALF >> 4), idesc, 1u);
+          tc_mma_tf32_ts(d_tmem, a_lo, b_hi, idesc, 1u);
+          if (kc < KCH - 1 || p.tail_steps == 2) {
+            tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
+            tc_mma_tf32_ts(d_tmem, a_hi + 8, b_hi + ((TC_KSTEP + TC_HALF) >> 4), idesc, 1u);
+            tc_mma_tf32_ts(d_tmem, a_lo + 8, b_hi + (TC_KSTEP >> 4), idesc, 1u);
           }
-          if (timing) { const long long c1 = clock64(); t_mma += c1 - c0; c0 = c1; }
           tc_commit(&ctl.b_empty[st]);               // stage reusable once these MMAs have read it
-          if (timing) { const long long c1 = clock64(); t_commit += c1 - c0; c0 = c1; }
           a_hi += TC_KC; a_lo += TC_KC;
           if (++st == NST) { st = 0; ph ^= 1u; }
         }
@@ -471,13 +427,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
     uint32_t accph = 1;
     for (;;) {
       if (++buf == NACC || buf == 0) { buf = 0; accph ^= 1u; }
+      // the next accumulator is not ready: use the time to compact this warp's fuller rows (tighter
+      // thresholds earlier, and no bursts of compactions on the critical path later)
+      while (!__all_sync(0xffffffffu, mbar_test(&ctl.acc_full[buf], accph))) {
+        const unsigned fuller = __ballot_sync(0xffffffffu, ctl.cnt[row] > p.k_keep + TC_IDLE_MARGIN);
+        if (!fuller) break;
+        const int l = __ffs(fuller) - 1;
+        tc_compact_row(&ctl, lists + (quarter * 32 + l) * TC_LSTRIDE, quarter * 32 + l, p.k_keep, lane);
+        compacted_any = true;
+      }
       mbar_wait(&ctl.acc_full[buf], accph);
       tc_fence_after();
       const int tile = ctl.acc_tile[buf];
       if (tile < 0) break;
       mbar_wait(&ctl.yn_full[buf], accph);
       const int colbase = tile * TC_BN;
-      if ((p.debug & 7) == 1 || (p.debug & 7) >= 3) {
+      if (p.debug == 1) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl.acc_empty[buf]);
@@ -501,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
           q[j4] = fminf(fminf(s0, s1), fminf(s2, s3));
         }
         const float m = fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])), fminf(fminf(q[4], q[5]), fminf(q[6], q[7])));
-        if (__any_sync(0xffffffffu, m < thr) && (p.debug & 7) != 2) {
+        if (__any_sync(0xffffffffu, m < thr) && p.debug != 2) {
           // room for this step's (at most 32) pushes: rows above TC_HIGH are compacted first
           int c = ctl.cnt[row];
           const unsigned need = __ballot_sync(0xffffffffu, c > TC_HIGH);
