@@ -112,6 +112,13 @@ int pb200_knn_direct_f64(const double* data, long long n, int m, const double* q
  * positions in the sorted order; tiles_scanned (optional) counts visited 128-point tiles. */
 int pb200_knn_sorted_f64(const double* data, long long n, int m, int q0, int nq, int k, int* out_idx,
                          double* out_dist, unsigned long long* tiles_scanned, void* stream);
+/* Same search on cells stored in any locality-preserving order (Morton curve of the leading coordinates),
+ * with exact pruning by the bounding boxes of the 128-row tiles (pb200_tile_boxes_md: box_lo / box_hi
+ * [ceil(n/128)][m]); indices are positions in the stored order. */
+int pb200_tile_boxes_md(const double* data, long long n, int m, double* box_lo, double* box_hi, void* stream);
+int pb200_knn_boxed_f64(const double* data, long long n, int m, int q0, int nq, int k, const double* box_lo,
+                        const double* box_hi, int* out_idx, double* out_dist, unsigned long long* tiles_scanned,
+                        void* stream);
 /* locality ordering: perm[i] = index of the i-th smallest data[:, col]; inv[perm[i]] = i */
 long long pb200_argsort_scratch_bytes(long long n);
 int pb200_argsort_col_f64(const double* data, long long n, int m, int col, int* perm, int* inv, void* scratch,
@@ -137,7 +144,8 @@ int pb200_symmetrize_phase2(long long n, const long long* off, const int* indptr
                             const double* tval, int* indices, double* data, void* stream);
 
 int pb200_csr_row_sums(const int* indptr, const double* data, long long n, double* out, void* stream);
-/* op 0: 1/v (v != 0); op 1: v^p (v != 0); op 2: 1/sqrt(v) (v > 0, else 0); op 3: sqrt(v) */
+/* op 0: 1/v (v != 0); op 1: v^p (v != 0); op 2: 1/sqrt(v) (v > 0, else 0); op 3: sqrt(v);
+ * op 4: 0 where v < p (PResults clips fate probabilities below 0.01, src/palantir/presults.py:34) */
 int pb200_vec_transform(double* v, long long n, int op, double p, void* stream);
 /* out[e] = (left[row] * data[e]) * right[col]; left / right may be NULL */
 int pb200_csr_scale(const int* indptr, const int* indices, const double* data, long long n, const double* left,

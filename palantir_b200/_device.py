@@ -70,6 +70,60 @@ def to_host(*tensors: torch.Tensor):
     return arrs[0] if len(arrs) == 1 else arrs
 
 
+class HostCopy:
+    """Device -> host copies in flight on a side stream (see to_host_async)."""
+
+    def __init__(self, bufs, keep, stream):
+        self._bufs, self._keep, self._stream = bufs, keep, stream
+
+    def result(self):
+        """Wait for the copies; numpy arrays owning their page-locked buffers."""
+        if self._stream is not None:
+            self._stream.synchronize()
+        self._keep = None
+        arrs = [b.numpy() for b in self._bufs]
+        return arrs[0] if len(arrs) == 1 else arrs
+
+
+_COPY_STREAMS: dict = {}
+
+
+def to_host_async(*tensors: torch.Tensor) -> HostCopy:
+    """Start copying device tensors into page-locked host buffers on a side stream, ordered after
+    the work already queued on the current stream, and return at once: the DMA runs under whatever
+    is launched next (the kernel matrix goes home while the eigensolver runs).  ``.result()`` waits."""
+    tensors = [t.contiguous() for t in tensors]
+    if not tensors or not tensors[0].is_cuda:
+        return HostCopy([t.cpu() for t in tensors], None, None)
+    dev = tensors[0].device
+    side = _COPY_STREAMS.get(dev.index)
+    if side is None:
+        side = _COPY_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    bufs = []
+    with torch.cuda.stream(side):
+        for t in tensors:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            t.record_stream(side)
+            bufs.append(buf)
+    return HostCopy(bufs, tensors, side)
+
+
+def csr_to_host_async(c: "DeviceCSR", data: Optional[torch.Tensor] = None):
+    """csr_to_host with the transfer left in flight; call the returned function for the scipy matrix."""
+    from scipy.sparse import csr_matrix
+
+    h = to_host_async(c.data if data is None else data, c.indices, c.indptr)
+    n = c.n
+
+    def finish():
+        vals, indices, indptr = h.result()
+        return csr_matrix((vals, indices, indptr), shape=(n, n))
+
+    return finish
+
+
 def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
@@ -487,6 +541,7 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
         resid = np.abs(b[m - 1] * y_all[m - 1, order])
         theta, yvec = theta_all[order], y_all[:, order]
         info.update(steps=m, max_resid=float(resid.max()))
+        info.setdefault("history", []).append((m, float(resid.max())))
         exhausted = (m >= n) or (b[m - 1] <= 1e-14 * max(1.0, np.abs(theta_all).max()))
         if np.all(resid <= tol * np.maximum(np.abs(theta), 1e-3)) or exhausted:
             info["converged"] = True

@@ -95,6 +95,49 @@ def locality_order(dev: torch.Tensor, want_sorted: bool = True):
     return perm, inv, out
 
 
+def morton_order(dev: torch.Tensor):
+    """Order the cells along the Morton curve of their first three columns (the leading multiscale
+    components: the trajectory is a thin tube in that space, so consecutive cells are neighbours and
+    the 128-cell tiles have small bounding boxes).  Returns (perm, inv, ordered copy):
+    ordered[i] = dev[perm[i]], inv[perm[i]] = i."""
+    n, m = dev.shape
+    lib = _native.load()
+    mm = min(3, m)
+    proj = zeros((3, n), F64)
+    proj[:mm] = dev[:, :mm].t()
+    lo = proj.amin(dim=1).cpu()
+    hi = proj.amax(dim=1).cpu()
+    ext = float((hi - lo).max().item())
+    inv_cell = (2 ** 21 - 1) / ext if ext > 0.0 else 1.0
+    nbytes = int(lib.pb200_argsort_scratch_bytes(n))
+    scratch = empty((nbytes,), torch.uint8)
+    perm, inv = empty((n,), I32), empty((n,), I32)
+    call("pb200_morton_order", proj, n, float(lo[0]), float(lo[1]), float(lo[2]), float(inv_cell), perm, inv,
+         scratch, nbytes)
+    out = empty((n, m), F64)
+    call("pb200_permute_rows_f64", dev, n, m, perm, out)
+    return perm, inv, out
+
+
+def knn_table_boxed(work: torch.Tensor, knn: int):
+    """Self-including neighbour table of cells stored in a locality-preserving order (exact, pruned by
+    the bounding boxes of the 128-cell tiles); indices are stored positions; rows sharded across ranks."""
+    n, m = work.shape
+    if knn > n:
+        raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {knn}, n_samples_fit = {n}")
+    q0, nq = _dist.row_shard(n, 256)
+    ntiles = (n + 127) // 128
+    box_lo, box_hi = empty((ntiles, m), F64), empty((ntiles, m), F64)
+    idx = empty((nq, knn), I32)
+    dist = empty((nq, knn), F64)
+    scanned = zeros((1,), I64)
+    with stage("knn_direct"):
+        call("pb200_tile_boxes_md", work, n, m, box_lo, box_hi)
+        call("pb200_knn_boxed_f64", work, n, m, q0, nq, knn, box_lo, box_hi, idx, dist, scanned)
+    idx, dist = _dist.allgather_rows(idx, dist, n, 256)
+    return idx, dist, {"method": "direct-boxed", "flagged": 0, "scanned": scanned}
+
+
 def knn_table_sorted(dsort: torch.Tensor, knn: int):
     """Self-including neighbour table of cells already sorted along column 0 (exact, pruned);
     indices are sorted positions; rows sharded across ranks."""

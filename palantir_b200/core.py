@@ -65,8 +65,8 @@ def _boundary_positions(dev: torch.Tensor) -> np.ndarray:
 def _compute_pseudotime_device(dev: torch.Tensor, start_pos: int, knn: int, wp_pos: np.ndarray,
                                max_iterations: int):
     """core.py:353-401 on positions.  When sklearn would pick its kd-tree (<= 15 columns) the
-    stage runs on cells sorted along the first component (pruned exact kNN, L2-friendly
-    shortest paths).  Returns (pseudotime [N] in input order, D shard [rows, N] and colsum [N] in
+    stage runs on cells ordered along the Morton curve of the leading components (box-pruned exact
+    kNN, L2-friendly shortest paths).  Returns (pseudotime [N] in input order, D shard [rows, N] and colsum [N] in
     WORK order, row0, sdv, perm) with perm = None when work order == input order, else
     work[i] = input[perm[i]]."""
     print("Shortest path distances using {}-nearest neighbor graph...".format(knn))
@@ -76,8 +76,8 @@ def _compute_pseudotime_device(dev: torch.Tensor, start_pos: int, knn: int, wp_p
         raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {knn}, n_samples_fit = {n}")
     wp_pos = np.asarray(wp_pos, dtype=np.int64)
     if not dv.sklearn_uses_brute(n, m, knn):
-        perm, inv, work = dc.locality_order(dev)
-        idx, dist, kstats = dc.knn_table_sorted(work, knn)
+        perm, inv, work = dc.morton_order(dev)
+        idx, dist, kstats = dc.knn_table_boxed(work, knn)
         inv_h = inv.cpu().numpy().astype(np.int64)
         start_w, wp_w = int(inv_h[start_pos]), inv_h[wp_pos]
     else:
@@ -273,6 +273,9 @@ def run_palantir(data, early_cell, terminal_states=None, knn: int = 30, num_wayp
     if perm is not None:
         fates_dev, ent_dev = dc.unpermute_rows(fates_dev, perm), dc.unpermute_rows(ent_dev, perm)
 
+    # PResults zeroes probabilities below 1 % (presults.py:34); the entropy above is of the unclipped rows
+    if fates_dev.numel():
+        dv.call("pb200_vec_transform", fates_dev, fates_dev.numel(), 4, 0.01)
     pt_h, fates_h, ent_h = dv.to_host(pt_dev, fates_dev, ent_dev)
     pseudotime = pd.Series(pt_h, index=index)
     branch_probs = pd.DataFrame(fates_h, index=index, columns=term_labels)
@@ -281,7 +284,7 @@ def run_palantir(data, early_cell, terminal_states=None, knn: int = 30, num_wayp
     else:
         ent = pd.Series(ent_h, index=index)
 
-    pr_res = PResults(pseudotime, ent, branch_probs, waypoints)
+    pr_res = PResults(pseudotime, ent, branch_probs, waypoints, _clipped=True)
 
     if is_anndata(data):
         data.obs[pseudo_time_key] = pseudotime

@@ -265,7 +265,8 @@ __global__ void csr_row_sums_kernel(const int* __restrict__ indptr, const double
   out[i] = s;
 }
 
-// op 0: v[i] = v != 0 ? 1/v : v ;  op 1: v != 0 ? v^p : v ; op 2: v > 0 ? 1/sqrt(v) : 0 ; op 3: sqrt(v)
+// op 0: v[i] = v != 0 ? 1/v : v ;  op 1: v != 0 ? v^p : v ; op 2: v > 0 ? 1/sqrt(v) : 0 ; op 3: sqrt(v) ;
+// op 4: v < p ? 0 : v
 __global__ void vec_transform_kernel(double* __restrict__ v, long long n, int op, double p) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -273,7 +274,8 @@ __global__ void vec_transform_kernel(double* __restrict__ v, long long n, int op
   if (op == 0) v[i] = x != 0.0 ? 1.0 / x : x;
   else if (op == 1) v[i] = x != 0.0 ? pow(x, p) : x;
   else if (op == 2) v[i] = x > 0.0 ? 1.0 / sqrt(x) : 0.0;
-  else v[i] = sqrt(x);
+  else if (op == 3) v[i] = sqrt(x);
+  else v[i] = x < p ? 0.0 : x;
 }
 
 // counts entries (i,j,v) that have no mirror (j,i,v') within tolerance; needs sorted columns

@@ -194,6 +194,190 @@ __global__ void __launch_bounds__(KD_ROWS) knn_sorted_kernel(const double* __res
   if (tid == 0 && tiles_scanned) atomicAdd(tiles_scanned, scanned);
 }
 
+
+// Per-tile bounding boxes (all m coordinates) of 128-point tiles of row-major data.
+__global__ void __launch_bounds__(128) tile_boxes_md_kernel(const double* __restrict__ data, long long n, int m,
+                                                            double* __restrict__ box_lo, double* __restrict__ box_hi) {
+  const long long t = blockIdx.x;
+  const long long i = t * KD_TILE + threadIdx.x;
+  __shared__ double s_lo[4][16], s_hi[4][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = 0; c < m; ++c) {
+    double lo = INFINITY, hi = -INFINITY;
+    if (i < n) lo = hi = data[i * m + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { s_lo[warp][c] = lo; s_hi[warp][c] = hi; }
+  }
+  __syncthreads();
+  if (threadIdx.x < m) {
+    const int c = threadIdx.x;
+    box_lo[t * m + c] = fmin(fmin(s_lo[0][c], s_lo[1][c]), fmin(s_lo[2][c], s_lo[3][c]));
+    box_hi[t * m + c] = fmax(fmax(s_hi[0][c], s_hi[1][c]), fmax(s_hi[2][c], s_hi[3][c]));
+  }
+}
+
+// outward sequence of tiles around tile q: q, q-1, q+1, q-2, ... then the remaining side
+__device__ __forceinline__ long long kd_tile_of(long long s, long long q, long long T) {
+  const long long R = T - q, L = q;
+  const long long mn = R < L ? R : L;
+  if (s < 2 * mn) return (s & 1) ? q - 1 - (s >> 1) : q + (s >> 1);
+  const long long rest = s - 2 * mn;
+  return R > L ? q + mn + rest : q - 1 - mn - rest;
+}
+
+// Same search on cells in ANY locality-preserving order (here: the Morton curve of the leading
+// coordinates) with exact pruning by bounding boxes: a 128-point reference tile is skipped when the
+// squared gap between its box and the box of the CTA's 128 query rows is >= the largest current k-th
+// squared distance of those rows, and a single row skips a tile whose box is no closer than its own
+// k-th distance.  The gap is accumulated exactly like a distance (coordinate order, separate
+// multiply and add, round-to-nearest), and every operation in that chain is monotone, so the
+// computed gap never exceeds the computed distance to any point of the box: nothing is lost.
+template <int M>
+__global__ void __launch_bounds__(KD_ROWS) knn_boxed_kernel(const double* __restrict__ data, long long n, int q0,
+                                                            int nq, int k, const double* __restrict__ box_lo,
+                                                            const double* __restrict__ box_hi,
+                                                            int* __restrict__ out_idx, double* __restrict__ out_dist,
+                                                            unsigned long long* __restrict__ tiles_scanned) {
+  __shared__ double tile[KD_TILE][M];
+  __shared__ double s_qlo[M], s_qhi[M], s_tlo[M], s_thi[M];
+  __shared__ double s_red[KD_ROWS / 32];
+  __shared__ double s_maxworst;
+  __shared__ int s_acc[KD_ROWS];
+  __shared__ int s_wcnt[KD_ROWS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long qb0 = (long long)q0 + (long long)blockIdx.x * KD_ROWS;
+  const long long q = qb0 + tid;
+  const bool active = (long long)blockIdx.x * KD_ROWS + tid < nq;
+  const long long ntiles = (n + KD_TILE - 1) / KD_TILE;
+  const long long qtile = qb0 / KD_TILE;
+  double x[M];
+  {
+    const long long src = active ? q : qb0;
+#pragma unroll
+    for (int c = 0; c < M; ++c) x[c] = data[src * M + c];
+  }
+  if (tid < M) { s_qlo[tid] = box_lo[qtile * M + tid]; s_qhi[tid] = box_hi[qtile * M + tid]; }
+  double bd[KD_KMAX];
+  int bi[KD_KMAX];
+  for (int s = 0; s < k; ++s) { bd[s] = INFINITY; bi[s] = -1; }
+  double worst = INFINITY;
+  if (tid == 0) s_maxworst = INFINITY;
+  __syncthreads();
+  unsigned long long scanned = 0;
+  for (long long base = 0; base < ntiles; base += KD_ROWS) {
+    // ---- 128 candidate tiles of the outward sequence, one per thread ----
+    const long long sidx = base + tid;
+    long long cand = -1;
+    bool ok = false;
+    if (sidx < ntiles) {
+      cand = kd_tile_of(sidx, qtile, ntiles);
+      double g2 = 0.0;
+#pragma unroll
+      for (int c = 0; c < M; ++c) {
+        const double d1 = __dsub_rn(box_lo[cand * M + c], s_qhi[c]);
+        const double d2 = __dsub_rn(s_qlo[c], box_hi[cand * M + c]);
+        double gp = d1 > d2 ? d1 : d2;
+        gp = gp > 0.0 ? gp : 0.0;
+        g2 = __dadd_rn(g2, __dmul_rn(gp, gp));
+      }
+      ok = g2 < s_maxworst;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < KD_ROWS / 32; ++w) { off += w < warp ? s_wcnt[w] : 0; total += s_wcnt[w]; }
+    if (ok) s_acc[off + __popc(bal & ((1u << lane) - 1u))] = (int)cand;
+    __syncthreads();
+    // ---- scan the accepted tiles (bound re-checked: it tightens as the scan proceeds) ----
+    for (int a = 0; a < total; ++a) {
+      const long long t = s_acc[a];
+      const long long t0 = t * KD_TILE;
+      __syncthreads();
+      if (tid < M) { s_tlo[tid] = box_lo[t * M + tid]; s_thi[tid] = box_hi[t * M + tid]; }
+      __syncthreads();
+      double gq = 0.0, gr = 0.0;      // gap of the tile box to the CTA's box and to this row
+#pragma unroll
+      for (int c = 0; c < M; ++c) {
+        const double d1 = __dsub_rn(s_tlo[c], s_qhi[c]);
+        const double d2 = __dsub_rn(s_qlo[c], s_thi[c]);
+        double gp = d1 > d2 ? d1 : d2;
+        gp = gp > 0.0 ? gp : 0.0;
+        gq = __dadd_rn(gq, __dmul_rn(gp, gp));
+        const double e1 = __dsub_rn(s_tlo[c], x[c]);
+        const double e2 = __dsub_rn(x[c], s_thi[c]);
+        double ep = e1 > e2 ? e1 : e2;
+        ep = ep > 0.0 ? ep : 0.0;
+        gr = __dadd_rn(gr, __dmul_rn(ep, ep));
+      }
+      if (!(gq < s_maxworst)) continue;          // uniform: every thread reads the same values
+      for (int e = tid; e < KD_TILE * M; e += KD_ROWS) {
+        const long long g = t0 * M + e;
+        (&tile[0][0])[e] = g < n * M ? data[g] : 0.0;
+      }
+      __syncthreads();
+      ++scanned;
+      const int lim = (int)((n - t0) < KD_TILE ? (n - t0) : KD_TILE);
+      if (active && gr < worst) {
+#pragma unroll 4
+        for (int j = 0; j < lim; ++j) {
+          double r = 0.0;
+#pragma unroll
+          for (int c = 0; c < M; ++c) {
+            const double df = __dsub_rn(x[c], tile[j][c]);
+            r = __dadd_rn(r, __dmul_rn(df, df));
+          }
+          if (r < worst) {
+            int pos = k - 1;
+            while (pos > 0 && bd[pos - 1] > r) {
+              bd[pos] = bd[pos - 1];
+              bi[pos] = bi[pos - 1];
+              --pos;
+            }
+            bd[pos] = r;
+            bi[pos] = (int)(t0 + j);
+            worst = bd[k - 1];
+          }
+        }
+      }
+      double w = active ? worst : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) w = fmax(w, __shfl_xor_sync(0xffffffffu, w, o));
+      if (lane == 0) s_red[warp] = w;
+      __syncthreads();
+      if (tid == 0) {
+        double mw = s_red[0];
+        for (int qq = 1; qq < KD_ROWS / 32; ++qq) mw = fmax(mw, s_red[qq]);
+        s_maxworst = mw;
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    const long long row = (long long)blockIdx.x * KD_ROWS + tid;
+    for (int s = 0; s < k; ++s) {
+      out_idx[row * k + s] = bi[s];
+      out_dist[row * k + s] = sqrt(bd[s]);
+    }
+  }
+  if (tid == 0 && tiles_scanned) atomicAdd(tiles_scanned, scanned);
+}
+
+template <int M>
+static int launch_boxed(const double* data, long long n, int q0, int nq, int k, const double* box_lo,
+                        const double* box_hi, int* out_idx, double* out_dist, unsigned long long* tiles_scanned,
+                        cudaStream_t st) {
+  knn_boxed_kernel<M><<<div_up(nq, KD_ROWS), KD_ROWS, 0, st>>>(data, n, q0, nq, k, box_lo, box_hi, out_idx, out_dist,
+                                                             tiles_scanned);
+  PB_CHECK_LAUNCH("knn_boxed_kernel");
+  return 0;
+}
+
 template <int M>
 static int launch_sorted(const double* data, long long n, int q0, int nq, int k, int* out_idx, double* out_dist,
                          unsigned long long* tiles_scanned, cudaStream_t st) {
@@ -249,6 +433,37 @@ int pb200_knn_sorted_f64(const double* data, long long n, int m, int q0, int nq,
   if (nq <= 0) return 0;
   switch (m) {
 #define PB_CASE(M) case M: return launch_sorted<M>(data, n, q0, nq, k, out_idx, out_dist, tiles_scanned, st);
+    PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
+    PB_CASE(9) PB_CASE(10) PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15) PB_CASE(16)
+#undef PB_CASE
+  }
+  return -1;
+}
+
+// Bounding boxes box_lo / box_hi [ceil(n/128)][m] of the 128-row tiles of data (n x m, row-major).
+int pb200_tile_boxes_md(const double* data, long long n, int m, double* box_lo, double* box_hi, void* stream) {
+  if (m < 1 || m > 16) { set_error_msg("pb200_tile_boxes_md: need 1 <= m <= 16"); return -1; }
+  if (n <= 0) return 0;
+  tile_boxes_md_kernel<<<div_up(n, KD_TILE), KD_TILE, 0, (cudaStream_t)stream>>>(data, n, m, box_lo, box_hi);
+  PB_CHECK_LAUNCH("tile_boxes_md_kernel");
+  return 0;
+}
+
+// Same result as pb200_knn_direct_f64 on cells stored in a locality-preserving order (any order is
+// correct; a space-filling curve makes the boxes small), with exact bounding-box pruning; box_lo /
+// box_hi from pb200_tile_boxes_md; rows q0..q0+nq-1 are the queries (q0 % 128 == 0); indices refer
+// to the stored order.
+int pb200_knn_boxed_f64(const double* data, long long n, int m, int q0, int nq, int k, const double* box_lo,
+                        const double* box_hi, int* out_idx, double* out_dist, unsigned long long* tiles_scanned,
+                        void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m < 1 || m > 16 || k < 1 || k > KD_KMAX || k > n || q0 % KD_TILE != 0) {
+    set_error_msg("pb200_knn_boxed_f64: need 1 <= m <= 16, 1 <= k <= min(64, n), q0 % 128 == 0");
+    return -1;
+  }
+  if (nq <= 0) return 0;
+  switch (m) {
+#define PB_CASE(M) case M: return launch_boxed<M>(data, n, q0, nq, k, box_lo, box_hi, out_idx, out_dist, tiles_scanned, st);
     PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
     PB_CASE(9) PB_CASE(10) PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15) PB_CASE(16)
 #undef PB_CASE

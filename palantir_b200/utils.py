@@ -75,7 +75,9 @@ def compute_kernel(data, knn: int = 30, alpha: float = 0, pca_key: str = "X_pca"
     return kernel
 
 
-def _diffusion_maps_device(kern: dv.DeviceCSR, n_components: int, seed):
+def _diffusion_maps_device(kern: dv.DeviceCSR, n_components: int, seed, t_home: Optional[list] = None):
+    """(T values, eigenvalues, eigenvectors) on the device.  With ``t_home`` (a list) the copy of T
+    to the host is started before the eigensolver and its finisher appended to the list."""
     n = kern.n
     if not dv.check_symmetric(kern):
         raise dv.NotSymmetricError(
@@ -88,6 +90,8 @@ def _diffusion_maps_device(kern: dv.DeviceCSR, n_components: int, seed):
     v0 = np.random.rand(n)
     start = dv.empty((n,), dv.F64)
     dv.call("pb200_vec_mul", dv.to_device(v0), dsq, start, n)
+    if t_home is not None:
+        t_home.append(dv.csr_to_host_async(kern, tvals))
     with dv.stage("eigensolver"):
         lam, U, info = dv.lanczos_topk(kern, svals, dis, start, n_components)
     LAST_INFO["lanczos"] = info
@@ -123,13 +127,26 @@ def run_diffusion_maps(data, n_components: int = 10, knn: int = 30, alpha: float
     if not isinstance(data_df, pd.DataFrame) and not issparse(data_df):
         raise ValueError("'data_df' should be a pd.DataFrame or AnnData")
     if not issparse(data_df):
-        kernel = compute_kernel(data_df, knn, alpha, backend=kernel_backend)
+        # same results as compute_kernel + diffusion_maps_from_kernel, with the two sparse matrices
+        # travelling to the host while the eigensolver runs
+        if kernel_backend not in {"scanpy", "sklearn"}:
+            raise ValueError("backend must be one of {'scanpy', 'sklearn'}")
+        if knn is None or int(knn) <= 0:
+            raise ValueError("knn must be a positive integer")
+        kern = _compute_kernel_device(data_df.values, int(knn), float(alpha))
+        k_home = dv.csr_to_host_async(kern)
+        t_home: list = []
+        tvals, lam, U = _diffusion_maps_device(kern, n_components, seed, t_home)
+        vecs = pd.DataFrame(dv.to_host(U), copy=False)
+        kernel = k_home()
+        kernel._pb200_device = kern
+        res = {"T": t_home[0](), "EigenVectors": vecs, "EigenValues": pd.Series(lam)}
     else:
         warn("'data' is a sparse matrix and will be interpreted as kernel. "
              "To avoid this warning compute diffusion maps from a precompued kernel using "
              "palantir.utils.diffusion_maps_from_kernel().")
         kernel = data_df
-    res = diffusion_maps_from_kernel(kernel, n_components, seed)
+        res = diffusion_maps_from_kernel(kernel, n_components, seed)
     res["kernel"] = kernel
     if not issparse(data_df):
         res["EigenVectors"].index = data_df.index
@@ -165,9 +182,11 @@ def determine_multiscale_space(dm_res, n_eigs: Union[int, None] = None, eigval_k
             n_eigs = np.argsort(gaps)[-2] + 1
         if n_eigs < 3:
             n_eigs = 3
-    use = list(range(1, n_eigs))
-    ev = np.ravel(np.asarray(d["EigenValues"])[use])
-    out = pd.DataFrame(d["EigenVectors"].values[:, use] * (ev / (1 - ev)), index=d["EigenVectors"].index)
+    n_eigs = int(n_eigs)
+    ev = np.ravel(np.asarray(d["EigenValues"]))[1:n_eigs]
+    # columns 1..n_eigs-1 (utils.py:905-908); a slice, so the product is the only pass over the data
+    out = pd.DataFrame(d["EigenVectors"].values[:, 1:n_eigs] * (ev / (1 - ev)), index=d["EigenVectors"].index,
+                       copy=False)
     if is_anndata(dm_res):
         dm_res.obsm[out_key] = out.values
     return out

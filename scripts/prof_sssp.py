@@ -13,8 +13,8 @@ if "--bench" in sys.argv:
     x, info = synth_branching(n, 100)
     out = pipeline.run_device(dv.to_device(x), info["early"], list(info["terminals"].values()))
     data_t = dc.minmax_scale(out["multiscale"])
-    perm, inv, work = dc.locality_order(data_t)
-    idx, dist, st = dc.knn_table_sorted(work, 30)
+    perm, inv, work = dc.morton_order(data_t)
+    idx, dist, st = dc.knn_table_boxed(work, 30)
     g = dc.undirected_graph(idx, dist)
     src = dv.to_device(inv.cpu().numpy().astype(np.int64)[out["waypoints"]])
     lib = _native.load()
@@ -28,8 +28,8 @@ if "--bench" not in sys.argv:
     data = np.stack([t, np.sin(3 * t) * 0.5 + 0.5, np.cos(5 * t) * 0.5 + 0.5, t ** 2, np.sqrt(t), 0.5 + 0.3 * np.sin(9 * t)], 1)
     data += rng.normal(size=data.shape) * 2e-3
     dev = dv.to_device(np.ascontiguousarray(data))
-    perm, inv, work = dc.locality_order(dev)
-    idx, dist, st = dc.knn_table_sorted(work, 30)
+    perm, inv, work = dc.morton_order(dev)
+    idx, dist, st = dc.knn_table_boxed(work, 30)
     g = dc.undirected_graph(idx, dist)
     src = dv.to_device(rng.choice(n, 1198, replace=False).astype(np.int64))
     lib = _native.load()

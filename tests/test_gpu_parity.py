@@ -194,6 +194,34 @@ def test_run_diffusion_maps_anndata_keys(pb):
 
 
 # ------------------------------------------------------------------ run_palantir
+@pytest.mark.parametrize("n,m,k", [(5000, 5, 30), (1000, 3, 10), (777, 1, 5), (4100, 9, 31), (300, 2, 30)])
+def test_boxed_low_dimensional_knn_matches_sklearn_kd_tree(pb, n, m, k):
+    """The multiscale-space search (core.py:355-356): Morton order + bounding-box pruning must return
+    sklearn's kd-tree neighbours with bit-equal distances (direct differences in FP64)."""
+    import torch
+    from sklearn.neighbors import NearestNeighbors
+    from palantir_b200 import _device as dv, _device_core as dc
+
+    rng = np.random.default_rng(n + m)
+    t = rng.random(n)
+    data = np.stack([np.sin((c + 1) * t) + 0.01 * rng.normal(size=n) for c in range(m)], 1)   # a noisy curve
+    dev = dv.to_device(np.ascontiguousarray(data))
+    perm, inv, work = dc.morton_order(dev)
+    idx, dist, st = dc.knn_table_boxed(work, k)
+    perm_h = perm.cpu().numpy()
+    assert sorted(perm_h.tolist()) == list(range(n))
+    got_idx = np.empty((n, k), np.int64)
+    got_dist = np.empty((n, k))
+    got_idx[perm_h] = perm_h[idx.cpu().numpy()]
+    got_dist[perm_h] = dist.cpu().numpy()
+    rd, ri = NearestNeighbors(n_neighbors=k, algorithm="kd_tree").fit(data).kneighbors(data)
+    assert np.array_equal(got_dist, rd)
+    rows_equal = (np.sort(got_idx, 1) == np.sort(ri, 1)).all(1)
+    ties = np.array([len(np.unique(r)) < k for r in rd])
+    assert np.all(rows_equal | ties)
+    assert int(st["scanned"].item()) <= ((n + 127) // 128) ** 2
+
+
 def test_max_min_sampling_known_answer(pb):
     z = golden("ref_known_answers.npz")
     wp = pb.core._max_min_sampling(pd.DataFrame(z["mm_data"]), num_waypoints=9, seed=0)
