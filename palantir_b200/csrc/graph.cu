@@ -46,9 +46,21 @@ __global__ void uf_hook_kernel(const int* __restrict__ indptr, const int* __rest
   }
 }
 
+// Final labels.  The walk must not write: a path-halving store that was decided before another
+// thread published its final label would overwrite that label with an inner node of the tree
+// (seen as 1-6 "unreachable" cells per million, different on every run).  Read-only walks see
+// either the old parent or the root, and both lead to the root.
 __global__ void uf_compress_kernel(int* parent, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) parent[i] = uf_find(parent, (int)i);
+  if (i >= n) return;
+  volatile int* vp = parent;
+  int x = (int)i;
+  for (;;) {
+    const int p = vp[x];
+    if (p == x) break;
+    x = p;
+  }
+  vp[i] = x;
 }
 
 __global__ void count_other_label_kernel(const int* __restrict__ label, long long n, long long ref,

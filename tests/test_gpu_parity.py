@@ -319,6 +319,40 @@ def test_sssp_bit_exact_vs_scipy_dijkstra(pb):
         assert np.array_equal(D.cpu().numpy(), ref)                  # +inf where unreachable, bit-equal elsewhere
 
 
+def test_graph_components_vs_scipy_repeatable(pb):
+    """Reachability labels (core.py:806-817) on a graph with deep trees and a few components, five
+    times: the labels must be the component's smallest index every time (a racing path-halving store
+    once left inner tree nodes as labels for a handful of cells per million)."""
+    import torch
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from palantir_b200 import _device as dv
+
+    rng = np.random.default_rng(5)
+    n = 400_000
+    cuts = np.sort(rng.choice(np.arange(1, n), 6, replace=False))
+    a = np.arange(n - 1)
+    keep = ~np.isin(a + 1, cuts)                                  # paths 0..c1-1, c1..c2-1, ...
+    src, dst = a[keep], a[keep] + 1
+    comp_of = np.searchsorted(cuts, np.arange(n), side="right")
+    e1 = rng.integers(0, n, 3 * n)
+    e2 = rng.integers(0, n, 3 * n)
+    same = comp_of[e1] == comp_of[e2]                              # random chords inside a component
+    src, dst = np.concatenate([src, e1[same]]), np.concatenate([dst, e2[same]])
+    m = coo_matrix((np.ones(2 * len(src)), (np.concatenate([src, dst]), np.concatenate([dst, src]))), shape=(n, n)).tocsr()
+    m.sum_duplicates()
+    ncomp, ref = connected_components(m, directed=False)
+    assert ncomp == 7
+    first = np.full(ncomp, n, dtype=np.int64)
+    np.minimum.at(first, ref, np.arange(n))
+    want = first[ref]
+    indptr, indices = dv.to_device(m.indptr.astype(np.int32)), dv.to_device(m.indices.astype(np.int32))
+    label = dv.empty((n,), dv.I32)
+    for _ in range(5):
+        dv.call("pb200_graph_components", indptr, indices, n, label)
+        assert np.array_equal(label.cpu().numpy(), want)
+
+
 def test_connect_graph_reconnects_like_the_reference(pb, po):
     rng = np.random.default_rng(4)
     a = rng.normal(size=(300, 4))
