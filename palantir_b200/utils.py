@@ -27,6 +27,27 @@ __all__ = ["compute_kernel", "diffusion_maps_from_kernel", "run_diffusion_maps",
 LAST_INFO: dict = {}
 
 
+def _fingerprint(m: csr_matrix):
+    """Cheap identity of a host CSR matrix: buffer addresses, sizes and a strided sample of the values.
+    A cached device copy is used only while this still matches (a matrix edited in place -- rescaled,
+    thresholded -- is uploaded again)."""
+    d = m.data
+    return (m.shape, m.nnz, d.ctypes.data, m.indices.ctypes.data, m.indptr.ctypes.data,
+            float(d[::4099].sum()), float(d[:2048].sum()), float(d[-2048:].sum()))
+
+
+def _remember_device_copy(kernel: csr_matrix, kern: "dv.DeviceCSR") -> None:
+    kernel._pb200_device = (kern, _fingerprint(kernel))
+
+
+def _device_copy_of(kernel) -> Optional["dv.DeviceCSR"]:
+    hit = getattr(kernel, "_pb200_device", None)
+    if hit is None:
+        return None
+    kern, fp = hit
+    return kern if fp == _fingerprint(kernel) else None
+
+
 def _knn_table(values: np.ndarray, n_neighbors: int):
     """Full neighbour table on the device, query rows sharded across ranks when a
     process group is up (one process per GPU; allgather of the row shards)."""
@@ -69,7 +90,7 @@ def compute_kernel(data, knn: int = 30, alpha: float = 0, pca_key: str = "X_pca"
     values = data_df.values if isinstance(data_df, pd.DataFrame) else np.asarray(data_df)
     kern = _compute_kernel_device(values, int(knn), float(alpha))
     kernel = dv.csr_to_host(kern)
-    kernel._pb200_device = kern          # lets run_diffusion_maps skip the re-upload
+    _remember_device_copy(kernel, kern)  # lets diffusion_maps_from_kernel skip the re-upload
     if is_anndata(data):
         data.obsp[kernel_key] = kernel
     return kernel
@@ -105,8 +126,8 @@ def diffusion_maps_from_kernel(kernel: csr_matrix, n_components: int = 10,
     eigenvectors of T as unit-L2 columns (DataFrame) and the eigenvalues, descending
     (Series).  Eigenvectors are converged (the reference stops ARPACK at tol 1e-4);
     their signs are arbitrary, as ARPACK's are."""
-    kern = getattr(kernel, "_pb200_device", None)
-    if kern is None or kern.n != kernel.shape[0] or kern.nnz != kernel.nnz:
+    kern = _device_copy_of(kernel)
+    if kern is None:
         kern = dv.csr_from_host(kernel)
     tvals, lam, U = _diffusion_maps_device(kern, n_components, seed)
     T = dv.csr_to_host(kern, tvals)
@@ -139,7 +160,7 @@ def run_diffusion_maps(data, n_components: int = 10, knn: int = 30, alpha: float
         tvals, lam, U = _diffusion_maps_device(kern, n_components, seed, t_home)
         vecs = pd.DataFrame(dv.to_host(U), copy=False)
         kernel = k_home()
-        kernel._pb200_device = kern
+        _remember_device_copy(kernel, kern)
         res = {"T": t_home[0](), "EigenVectors": vecs, "EigenValues": pd.Series(lam)}
     else:
         warn("'data' is a sparse matrix and will be interpreted as kernel. "

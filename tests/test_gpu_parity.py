@@ -177,6 +177,20 @@ def test_diffusion_maps_from_kernel_reference_tests(pb):
     assert pb.utils.determine_multiscale_space(r).shape[0] == 50
 
 
+def test_kernel_edited_in_place_is_uploaded_again(pb):
+    """compute_kernel leaves a device copy on the matrix it returns; editing the matrix in place must
+    not let diffusion_maps_from_kernel use the stale copy."""
+    z = golden("dm_f64_n600_d8.npz")
+    kernel = pb.utils.compute_kernel(pd.DataFrame(z["x"]), knn=int(z["knn"]))
+    kernel.data[::2] *= 0.25
+    sym = csr_matrix(kernel.maximum(kernel.T))          # fresh symmetric matrix, no device copy attached
+    kernel.data[:] = sym.data                           # same pattern: edit in place to the symmetric values
+    got = pb.utils.diffusion_maps_from_kernel(kernel, n_components=5, seed=0)
+    want = pb.utils.diffusion_maps_from_kernel(sym, n_components=5, seed=0)
+    assert np.allclose(got["EigenValues"].values, want["EigenValues"].values, rtol=0, atol=1e-12)
+    assert abs(got["T"] - want["T"]).max() < 1e-15
+
+
 def test_run_diffusion_maps_anndata_keys(pb):
     from palantir_b200.compat import AnnDataLike
 
