@@ -47,6 +47,12 @@ dc.SSSP_MODE = "csr"; lib.pb200_sssp_set_variant(4)
 Dref = run("csr v4 (128 thr)")
 if "--one" in sys.argv:
     sys.exit(0)
+if "--delta" in sys.argv:
+    dc.SSSP_MODE = "arcrec"; dc.SSSP_THREADS = None
+    for ns in (1198, 599, 300, 150):
+        for mult in (4.0, 8.0, 16.0, 32.0, 64.0):
+            run("auto", mult, nsrc=ns)
+    sys.exit(0)
 if "--variants" in sys.argv:
     for v in (2, 3, 5, 6, 7, 4):
         lib.pb200_sssp_set_variant(v)
