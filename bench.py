@@ -280,7 +280,10 @@ def run_gpu_arm(args):
         knn_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
         knn_roof = {"bound": "tensor", "kernel": "knn_candidates_tc_kernel (tcgen05.mma kind::tf32, 3xTF32 split)",
                     "achieved": knn_tf, "peak": knn_peak, "unit": "TFLOP/s", "frac": knn_tf / knn_peak if knn_tf else None,
-                    "traffic": None,
+                    # DRAM bytes per launch from the ncu --set full capture of this kernel on this workload
+                    # (profiles/r1_knn_candidates_ncu.md, knn_tc_final: 151.0 GB read + 0.35 GB written)
+                    "traffic": 1.513e11 if (n == 1_000_000 and d == 100 and world == 1) else None,
+                    "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the BF16 rate; of measured)"
                                     if "bf16_tflops" in peaks else "B200_PROFILING.md fallback 1590/2 TF/s (of fallback)"),
                     "algorithmic": "3 x 2*Nq*Nr*d8 TF32 FLOP per launch x fraction of 128x128 tiles visited (exact "
