@@ -495,6 +495,10 @@ def transition_and_symmetric(kern: DeviceCSR):
     return tvals, svals, dis, dsq
 
 
+# Gram-Schmidt pass of the Lanczos recurrence on an FP32 shadow of the basis (see pb200_lanczos_steps)
+LANCZOS_FP32_SHADOW = os.environ.get("PB200_LANCZOS_SHADOW", "1") != "0"
+
+
 def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start: torch.Tensor, k: int,
                  tol: float = 1e-11, batch: int = 20, max_basis: Optional[int] = None):
     """Largest-magnitude k eigenpairs of S (= those of T) by symmetric Lanczos with
@@ -516,21 +520,22 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
     ld = n
     nblk = n // 2048 + 1
     V = empty((max_basis + 1, ld), F64)
+    V32 = empty((max_basis + 1, ld), F32) if LANCZOS_FP32_SHADOW else None
     alpha = zeros((max_basis + 1,), F64)
     beta = zeros((max_basis + 2,), F64)
     w = empty((n,), F64)
     h = empty((max_basis + 1,), F64)
     partial = empty(((max_basis + 1) * nblk,), F64)
     tmp = empty((1,), F64)
-    call("pb200_lanczos_init", start, n, V, partial, tmp)
+    call("pb200_lanczos_init", start, n, V, V32, partial, tmp)
     m = 0
     info = {"converged": False}
     theta = yvec = None
     while m < max_basis:
         steps = min(batch, max_basis - m)
         with stage("lanczos_steps"):
-            call("pb200_lanczos_steps", kern.indptr, kern.indices, svals, n, nnz, V, ld, m, steps, alpha, beta, w,
-                 h, partial, tmp)
+            call("pb200_lanczos_steps", kern.indptr, kern.indices, svals, n, nnz, V, ld, V32, m, steps, alpha, beta,
+                 w, h, partial, tmp)
         m += steps
         if m < k + 1 and m < max_basis:
             continue

@@ -87,7 +87,8 @@ constexpr int VB = 256;        // threads
 constexpr int VCHUNK = 2048;   // elements per block (8 per thread)
 
 // partial[c * nblk + b] = sum_{i in chunk b} V[c][i] * w[i],  c = 0..m-1
-__global__ void __launch_bounds__(VB) multi_dot_kernel(const double* __restrict__ V, long long ldv, int m,
+template <typename TV>
+__global__ void __launch_bounds__(VB) multi_dot_kernel(const TV* __restrict__ V, long long ldv, int m,
                                                        const double* __restrict__ w, long long n,
                                                        double* __restrict__ partial) {
   __shared__ double red[VB / 32];
@@ -99,12 +100,12 @@ __global__ void __launch_bounds__(VB) multi_dot_kernel(const double* __restrict_
     wr[t] = i < n ? w[i] : 0.0;
   }
   for (int c = 0; c < m; ++c) {
-    const double* v = V + (long long)c * ldv;
+    const TV* v = V + (long long)c * ldv;
     double s = 0.0;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const long long i = base + threadIdx.x + (long long)t * VB;
-      if (i < n) s = fma(v[i], wr[t], s);
+      if (i < n) s = fma((double)v[i], wr[t], s);
     }
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -139,7 +140,8 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 }
 
 // w[i] -= sum_c h[c] V[c][i]
-__global__ void __launch_bounds__(VB) multi_axpy_kernel(const double* __restrict__ V, long long ldv, int m,
+template <typename TV>
+__global__ void __launch_bounds__(VB) multi_axpy_kernel(const TV* __restrict__ V, long long ldv, int m,
                                                         const double* __restrict__ h, double* __restrict__ w,
                                                         long long n) {
   extern __shared__ double hs[];
@@ -150,12 +152,12 @@ __global__ void __launch_bounds__(VB) multi_axpy_kernel(const double* __restrict
 #pragma unroll
   for (int t = 0; t < 8; ++t) acc[t] = 0.0;
   for (int c = 0; c < m; ++c) {
-    const double* v = V + (long long)c * ldv;
+    const TV* v = V + (long long)c * ldv;
     const double hc = hs[c];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const long long i = base + threadIdx.x + (long long)t * VB;
-      if (i < n) acc[t] = fma(hc, v[i], acc[t]);
+      if (i < n) acc[t] = fma(hc, (double)v[i], acc[t]);
     }
   }
 #pragma unroll
@@ -165,13 +167,18 @@ __global__ void __launch_bounds__(VB) multi_axpy_kernel(const double* __restrict
   }
 }
 
-// out[i] = w[i] / sqrt(*nrm2)    (also records sqrt(*nrm2) into *beta_out if given)
+// out[i] = w[i] / sqrt(*nrm2)    (also records sqrt(*nrm2) into *beta_out if given; out32 = FP32 shadow copy)
 __global__ void scale_by_norm_kernel(const double* __restrict__ w, const double* __restrict__ nrm2,
-                                     double* __restrict__ out, long long n, double* __restrict__ beta_out) {
+                                     double* __restrict__ out, float* __restrict__ out32, long long n,
+                                     double* __restrict__ beta_out) {
   const double b = sqrt(*nrm2);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && beta_out) *beta_out = b;
-  if (i < n) out[i] = b > 0.0 ? w[i] / b : 0.0;
+  if (i < n) {
+    const double v = b > 0.0 ? w[i] / b : 0.0;
+    out[i] = v;
+    if (out32) out32[i] = (float)v;
+  }
 }
 
 // h2[0] = beta[j] (0 when j == 0), h2[1] = alpha[j]
@@ -268,7 +275,7 @@ static int launch_spmv(const int* indptr, const int* indices, const double* vals
 
 static int nrm2_into(const double* w, long long n, double* partial, double* out, cudaStream_t st) {
   const int nblk = div_up(n, VCHUNK);
-  multi_dot_kernel<<<nblk, VB, 0, st>>>(w, 0, 1, w, n, partial);
+  multi_dot_kernel<double><<<nblk, VB, 0, st>>>(w, 0, 1, w, n, partial);
   PB_CHECK_LAUNCH("multi_dot_kernel(nrm2)");
   reduce_partials_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, out, nullptr);
   PB_CHECK_LAUNCH("reduce_partials_kernel(nrm2)");
@@ -295,22 +302,27 @@ int pb200_vec_mul(const double* a, const double* b, double* out, long long n, vo
   return 0;
 }
 
-// V[0] = w / |w|.   scratch: partial[div_up(n,2048)], tmp[1]
-int pb200_lanczos_init(const double* w, long long n, double* V0, double* partial, double* tmp, void* stream) {
+// V[0] = w / |w| (and its FP32 shadow V32[0] when given).   scratch: partial[div_up(n,2048)], tmp[1]
+int pb200_lanczos_init(const double* w, long long n, double* V0, float* V32_0, double* partial, double* tmp,
+                       void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   int rc = nrm2_into(w, n, partial, tmp, st);
   if (rc) return rc;
-  scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V0, n, nullptr);
+  scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V0, V32_0, n, nullptr);
   PB_CHECK_LAUNCH("scale_by_norm_kernel");
   return 0;
 }
 
 // Runs Lanczos steps j = j0 .. j0+nsteps-1 on the symmetric CSR matrix.
 // In: V[0..j0] (rows of length ldv >= n) orthonormal.  Out: alpha[j], beta[j+1], V[j+1].
+// V32 (optional, same leading dimension): FP32 shadow of the basis, kept up to date here and used for
+// the Gram-Schmidt pass -- what that pass removes are round-off-level components (|h| <~ 1e-13 after
+// the three-term recurrence), so the 6e-8 relative error of the shadow changes w by < 1e-20 while the
+// pass reads half the bytes.  The recurrence itself, alpha, beta and the Ritz vectors use the FP64 basis.
 // Scratch: w[n], h[mcap], partial[mcap * div_up(n,2048)], tmp[1].
 int pb200_lanczos_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
-                        double* V, long long ldv, int j0, int nsteps, double* alpha, double* beta, double* w,
-                        double* h, double* partial, double* tmp, void* stream) {
+                        double* V, long long ldv, float* V32, int j0, int nsteps, double* alpha, double* beta,
+                        double* w, double* h, double* partial, double* tmp, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = div_up(n, VCHUNK);
   for (int j = j0; j < j0 + nsteps; ++j) {
@@ -318,29 +330,32 @@ int pb200_lanczos_steps(const int* indptr, const int* indices, const double* val
     int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st);
     if (rc) return rc;
     // three-term recurrence: alpha_j = v_j . w;  w -= alpha_j v_j + beta_j v_{j-1}
-    multi_dot_kernel<<<nblk, VB, 0, st>>>(V + (long long)j * ldv, ldv, 1, w, n, partial);
+    multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V + (long long)j * ldv, ldv, 1, w, n, partial);
     PB_CHECK_LAUNCH("multi_dot_kernel(alpha)");
     reduce_partials_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, alpha + j, nullptr);
     PB_CHECK_LAUNCH("reduce_partials_kernel(alpha)");
     recurrence_coeffs_kernel<<<1, 32, 0, st>>>(alpha, beta, j, h);
     PB_CHECK_LAUNCH("recurrence_coeffs_kernel");
     if (j > 0)
-      multi_axpy_kernel<<<nblk, VB, sizeof(double) * 2, st>>>(V + (long long)(j - 1) * ldv, ldv, 2, h, w, n);
+      multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * 2, st>>>(V + (long long)(j - 1) * ldv, ldv, 2, h, w, n);
     else
-      multi_axpy_kernel<<<nblk, VB, sizeof(double) * 1, st>>>(V, ldv, 1, h + 1, w, n);
+      multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * 1, st>>>(V, ldv, 1, h + 1, w, n);
     PB_CHECK_LAUNCH("multi_axpy_kernel(recurrence)");
     // one full Gram-Schmidt pass against V[0..j]; its v_j component corrects alpha_j
-    multi_dot_kernel<<<nblk, VB, 0, st>>>(V, ldv, m, w, n, partial);
+    if (V32) multi_dot_kernel<float><<<nblk, VB, 0, st>>>(V32, ldv, m, w, n, partial);
+    else     multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V, ldv, m, w, n, partial);
     PB_CHECK_LAUNCH("multi_dot_kernel");
     reduce_partials_kernel<<<m, 256, 0, st>>>(partial, nblk, m, h, nullptr);
     PB_CHECK_LAUNCH("reduce_partials_kernel");
     reduce_partials_kernel<<<1, 32, 0, st>>>(h + j, 1, 1, tmp, alpha + j);
     PB_CHECK_LAUNCH("reduce_partials_kernel(alpha)");
-    multi_axpy_kernel<<<nblk, VB, sizeof(double) * m, st>>>(V, ldv, m, h, w, n);
+    if (V32) multi_axpy_kernel<float><<<nblk, VB, sizeof(double) * m, st>>>(V32, ldv, m, h, w, n);
+    else     multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * m, st>>>(V, ldv, m, h, w, n);
     PB_CHECK_LAUNCH("multi_axpy_kernel");
     rc = nrm2_into(w, n, partial, tmp, st);
     if (rc) return rc;
-    scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V + (long long)(j + 1) * ldv, n, beta + j + 1);
+    scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V + (long long)(j + 1) * ldv,
+                                                         V32 ? V32 + (long long)(j + 1) * ldv : nullptr, n, beta + j + 1);
     PB_CHECK_LAUNCH("scale_by_norm_kernel");
   }
   return 0;

@@ -7,6 +7,7 @@
 // L2-resident index window.  The sort itself is CUB's device radix sort on the
 // order-preserving bit pattern of the FP64 key (plumbing; the kernels that use the
 // order are hand-written).
+#include <cstdlib>
 #include "common.cuh"
 #include <cub/cub.cuh>
 
@@ -32,19 +33,52 @@ __device__ __forceinline__ unsigned long long spread3(unsigned long long x) {
   return x;
 }
 
-// 63-bit Morton key of three projections (structure of arrays proj[3][n]), isotropic cells
+// Index along the 3-D Hilbert curve of a point with 21-bit coordinates (Skilling's axes-to-transpose
+// construction: undo the excess rotations/reflections level by level, then Gray-encode), bits
+// interleaved with axis 0 most significant.  Unlike the Morton curve it has no jumps: consecutive
+// indices are always neighbouring cells, so 128-point tiles have compact bounding boxes.
+__device__ __forceinline__ unsigned long long hilbert_key3(unsigned int x0, unsigned int x1, unsigned int x2) {
+  unsigned int X[3] = {x0, x1, x2};
+  const unsigned int M = 1u << 20;
+  for (unsigned int Q = M; Q > 1; Q >>= 1) {
+    const unsigned int P = Q - 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (X[i] & Q) {
+        X[0] ^= P;
+      } else {
+        const unsigned int t = (X[0] ^ X[i]) & P;
+        X[0] ^= t;
+        X[i] ^= t;
+      }
+    }
+  }
+  X[1] ^= X[0];
+  X[2] ^= X[1];
+  unsigned int t = 0;
+  for (unsigned int Q = M; Q > 1; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
+}
+
+// 63-bit space-filling-curve key of three projections (structure of arrays proj[3][n]), isotropic cells
 __global__ void morton_keys_kernel(const double* __restrict__ proj, long long n, double lo0, double lo1, double lo2,
-                                   double inv_cell, unsigned long long* __restrict__ keys, int* __restrict__ iota) {
+                                   double inv_cell, int hilbert, unsigned long long* __restrict__ keys,
+                                   int* __restrict__ iota) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double lo[3] = {lo0, lo1, lo2};
   unsigned long long key = 0;
+  unsigned int c[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     double q = (proj[(long long)a * n + i] - lo[a]) * inv_cell;
     q = q < 0.0 ? 0.0 : (q > 2097151.0 ? 2097151.0 : q);
-    key |= spread3((unsigned long long)q) << (2 - a);
+    c[a] = (unsigned int)q;
+    key |= spread3((unsigned long long)c[a]) << (2 - a);
   }
+  if (hilbert) key = hilbert_key3(c[0], c[1], c[2]);
   keys[i] = key;
   iota[i] = (int)i;
 }
@@ -156,7 +190,9 @@ int pb200_morton_order(const double* proj, long long n, double lo0, double lo1, 
   int* iota = (int*)p;                               p += ((size_t)n * 4 + al - 1) / al * al;
   size_t temp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, temp, kin, kout, iota, perm, (int)n);
-  morton_keys_kernel<<<div_up(n, 256), 256, 0, st>>>(proj, n, lo0, lo1, lo2, inv_cell, kin, iota);
+  static int curve = -1;   // PB200_CURVE=hilbert: Hilbert instead of Z-order (measured at C3: 13.3 % vs 13.7 % of tiles visited, 143 vs 146 ms; not the default)
+  if (curve < 0) { const char* e = getenv("PB200_CURVE"); curve = (e && e[0] == 'h') ? 1 : 0; }
+  morton_keys_kernel<<<div_up(n, 256), 256, 0, st>>>(proj, n, lo0, lo1, lo2, inv_cell, curve, kin, iota);
   PB_CHECK_LAUNCH("morton_keys_kernel");
   PB_CHECK(cub::DeviceRadixSort::SortPairs((void*)p, temp, kin, kout, iota, perm, (int)n, 0, 64, st));
   invert_perm_kernel<<<div_up(n, 256), 256, 0, st>>>(perm, n, inv);
