@@ -50,6 +50,148 @@ __global__ void __launch_bounds__(256) csr_spmv_kernel(const int* __restrict__ i
   if (lane == 0) y[row] = s;
 }
 
+
+// ---------------------------------------------------------------------------
+// SpMV with the x window staged in shared memory, for matrices whose rows are in a
+// locality-preserving order (the kNN stage's Morton order: 70 % of the kernel's columns lie within
+// +-12 k of the row at 1 M cells).  The plain kernel above is bound by L1 gather wavefronts
+// (one 32 B sector per nonzero, ~2 cycles each per SM); here a persistent CTA walks a contiguous row
+// range in blocks of SW_R rows and keeps x[r0 - H, r0 + R + H) in a 192 KB ring in shared memory
+// (position = column mod SW_C), so those gathers become shared-memory reads; the R new columns of the
+// next block are fetched with cp.async while the current block is computed; columns outside the
+// window fall back to the global gather.
+// ---------------------------------------------------------------------------
+constexpr int SW_THREADS = 512;
+constexpr int SW_R = 1024;                 // rows per block
+constexpr int SW_C = 24576;                // ring capacity in doubles (192 KB)
+constexpr int SW_H = (SW_C - 2 * SW_R) / 2;   // halo on each side of the block: 11264 columns
+
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(SW_THREADS, 1) csr_spmv_window_kernel(const int* __restrict__ indptr,
+                                                                        const int* __restrict__ indices,
+                                                                        const double* __restrict__ vals,
+                                                                        const double* __restrict__ x,
+                                                                        double* __restrict__ y, long long n,
+                                                                        long long rows_per_cta) {
+  extern __shared__ __align__(16) double xs[];
+  const int tid = threadIdx.x, lane16 = tid & 15, grp = tid >> 4;       // 32 row groups of 16 lanes
+  const long long rb = (long long)blockIdx.x * rows_per_cta;
+  long long re = rb + rows_per_cta;
+  if (re > n) re = n;
+  if (rb >= n) return;
+  // first window
+  {
+    long long lo = rb - SW_H, hi = rb + SW_R + SW_H;
+    if (lo < 0) lo = 0;
+    if (hi > n) hi = n;
+    for (long long c = lo + tid; c < hi; c += SW_THREADS) cp_async8(&xs[c % SW_C], x + c);
+  }
+  for (long long r0 = rb; r0 < re; r0 += SW_R) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                     // window of this block complete, previous block done
+    {
+      // columns that only the NEXT block needs: they overwrite the slots of columns below this block's window
+      long long lo = r0 + SW_R + SW_H, hi = r0 + 2 * SW_R + SW_H;
+      if (hi > n) hi = n;
+      if (r0 + SW_R < re)
+        for (long long c = lo + tid; c < hi; c += SW_THREADS) cp_async8(&xs[c % SW_C], x + c);
+    }
+    // window [wlo, whi) of this block; ring position of column c = c - ring0, minus SW_C when that is >= SW_C
+    const int wlo = (int)(r0 - SW_H), whi = (int)(r0 + SW_R + SW_H);
+    const int ring0 = (int)((r0 >= SW_H ? (r0 - SW_H) / SW_C : 0) * SW_C);
+    long long rend = r0 + SW_R;
+    if (rend > re) rend = re;
+    // A group of 16 lanes takes FOUR consecutive rows at a time, four entries per lane and row (64 slots
+    // per row; longer rows loop), and issues every value / column load of the batch before the first
+    // gather, and every gather (one shared-memory and one global load per slot, the unused one at a
+    // harmless address: no branches) before the first multiply: 16 warps per SM have to cover the
+    // HBM latency with loads in flight, not with occupancy.
+    int bnd[5], bnd_next[5];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const long long rr = r0 + 4 * grp + u < rend ? r0 + 4 * grp + u : rend;
+      bnd_next[u] = __ldg(indptr + rr);
+    }
+    for (long long rbase = r0 + 4 * grp; rbase < rend; rbase += 4 * (SW_THREADS / 16)) {
+#pragma unroll
+      for (int u = 0; u < 5; ++u) bnd[u] = bnd_next[u];
+      {
+        const long long nb = rbase + 4 * (SW_THREADS / 16);     // the group's next batch: extents in flight meanwhile
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const long long rr = nb + u < rend ? nb + u : rend;
+          bnd_next[u] = __ldg(indptr + rr);
+        }
+      }
+      int c[4][4];
+      double v[4][4], xg[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int e = bnd[u] + lane16 + 16 * t;
+          const bool ok = e < bnd[u + 1];
+          c[u][t] = ok ? __ldg(indices + e) : -1;
+          v[u][t] = ok ? __ldg(vals + e) : 0.0;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int cc = c[u][t];
+          const bool inwin = cc >= wlo && cc < whi;
+          const bool outwin = cc >= 0 && !inwin;
+          int pos = cc - ring0;
+          pos = pos >= SW_C ? pos - SW_C : pos;
+          xg[u][t] = __ldg(x + (outwin ? cc : 0));
+          const double xsv = xs[inwin ? pos : 0];
+          v[u][t] *= inwin ? xsv : 1.0;
+          c[u][t] = outwin ? 1 : 0;
+        }
+      double acc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[u] = 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[u] += c[u][t] ? v[u][t] * xg[u][t] : v[u][t];
+        // rows with more than 64 entries (hubs of the symmetrised graph): plain loop for the rest
+        for (int e = bnd[u] + 64 + lane16; e < bnd[u + 1]; e += 16) {
+          const int cc = __ldg(indices + e);
+          acc[u] = fma(__ldg(vals + e), __ldg(x + cc), acc[u]);
+        }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o, 16);
+      if (lane16 < 4 && rbase + lane16 < rend)
+        y[rbase + lane16] = lane16 == 0 ? acc[0] : (lane16 == 1 ? acc[1] : (lane16 == 2 ? acc[2] : acc[3]));
+    }
+  }
+}
+
+// Relabel a CSR matrix: new row r' = old row perm[r'], new column = inv[old column]
+// (indptr_new = prefix sums of the permuted row lengths, supplied by the caller).  Columns inside a
+// row keep the old order (not sorted by new label; the SpMV does not need it).
+__global__ void __launch_bounds__(256) csr_permute_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
+                                                          const double* __restrict__ vals, long long n,
+                                                          const int* __restrict__ perm, const int* __restrict__ inv,
+                                                          const int* __restrict__ indptr_new,
+                                                          int* __restrict__ indices_new, double* __restrict__ vals_new) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= n) return;
+  const int old = perm[r];
+  const int b = indptr[old], len = indptr[old + 1] - b, nb = indptr_new[r];
+  for (int t = lane; t < len; t += 32) {
+    indices_new[nb + t] = inv[indices[b + t]];
+    vals_new[nb + t] = vals[b + t];
+  }
+}
+
 // SpMM for MAGIC: Y[n][g] (+)= A X[n][g], FP32 dense operands, FP64 CSR values
 // converted on the fly (the reference casts T^t to float32, utils.py:791).
 // One warp per row; lanes stride over the g columns (coalesced X row reads).
@@ -259,8 +401,26 @@ __global__ void col_scale_kernel(double* __restrict__ A, long long n, int kk, co
 
 using namespace pb200;
 
+static int launch_spmv_window(const int* indptr, const int* indices, const double* vals, const double* x, double* y,
+                              long long n, cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = SW_C * (int)sizeof(double);
+  if (!attr_set) {
+    PB_CHECK(cudaFuncSetAttribute(csr_spmv_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  // contiguous row ranges, a multiple of the block height, one CTA per SM
+  long long rows_per_cta = (n + kSMs - 1) / kSMs;
+  rows_per_cta = (rows_per_cta + SW_R - 1) / SW_R * SW_R;
+  const int grid = (int)((n + rows_per_cta - 1) / rows_per_cta);
+  csr_spmv_window_kernel<<<grid, SW_THREADS, smem, st>>>(indptr, indices, vals, x, y, n, rows_per_cta);
+  PB_CHECK_LAUNCH("csr_spmv_window_kernel");
+  return 0;
+}
+
 static int launch_spmv(const int* indptr, const int* indices, const double* vals, const double* x, double* y,
-                       long long n, long long nnz, cudaStream_t st) {
+                       long long n, long long nnz, cudaStream_t st, int windowed = 0) {
+  if (windowed && n >= 4 * SW_C) return launch_spmv_window(indptr, indices, vals, x, y, n, st);
   const double mean = n > 0 ? (double)nnz / (double)n : 0.0;
   if (mean > 24.0) {
     csr_spmv_kernel<16><<<div_up(n * 16, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n);
@@ -287,6 +447,23 @@ extern "C" {
 int pb200_csr_spmv_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
                        const double* x, double* y, void* stream) {
   return launch_spmv(indptr, indices, vals, x, y, n, nnz, (cudaStream_t)stream);
+}
+
+// y = A x for a matrix whose rows are in a locality-preserving order (see csr_spmv_window_kernel);
+// same result as pb200_csr_spmv_f64 up to the summation order inside a row.
+int pb200_csr_spmv_window_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                              const double* x, double* y, void* stream) {
+  return launch_spmv(indptr, indices, vals, x, y, n, nnz, (cudaStream_t)stream, 1);
+}
+
+// Relabelled copy of a CSR matrix: row r' = row perm[r'], columns mapped through inv; indptr_new given.
+int pb200_csr_permute(const int* indptr, const int* indices, const double* vals, long long n, const int* perm,
+                      const int* inv, const int* indptr_new, int* indices_new, double* vals_new, void* stream) {
+  if (n <= 0) return 0;
+  csr_permute_kernel<<<div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, vals, n, perm, inv, indptr_new,
+                                                                   indices_new, vals_new);
+  PB_CHECK_LAUNCH("csr_permute_kernel");
+  return 0;
 }
 
 int pb200_csr_spmm_f32(const int* indptr, const int* indices, const double* vals, long long n, const float* x,
@@ -319,15 +496,16 @@ int pb200_lanczos_init(const double* w, long long n, double* V0, float* V32_0, d
 // the Gram-Schmidt pass -- what that pass removes are round-off-level components (|h| <~ 1e-13 after
 // the three-term recurrence), so the 6e-8 relative error of the shadow changes w by < 1e-20 while the
 // pass reads half the bytes.  The recurrence itself, alpha, beta and the Ritz vectors use the FP64 basis.
+// windowed != 0: the matrix rows are in a locality-preserving order; use the shared-memory-window SpMV.
 // Scratch: w[n], h[mcap], partial[mcap * div_up(n,2048)], tmp[1].
 int pb200_lanczos_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
-                        double* V, long long ldv, float* V32, int j0, int nsteps, double* alpha, double* beta,
-                        double* w, double* h, double* partial, double* tmp, void* stream) {
+                        double* V, long long ldv, float* V32, int windowed, int j0, int nsteps, double* alpha,
+                        double* beta, double* w, double* h, double* partial, double* tmp, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = div_up(n, VCHUNK);
   for (int j = j0; j < j0 + nsteps; ++j) {
     const int m = j + 1;
-    int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st);
+    int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st, windowed);
     if (rc) return rc;
     // three-term recurrence: alpha_j = v_j . w;  w -= alpha_j v_j + beta_j v_{j-1}
     multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V + (long long)j * ldv, ldv, 1, w, n, partial);

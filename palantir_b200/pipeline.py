@@ -30,7 +30,9 @@ def run_device(x_dev: torch.Tensor, early_pos: int, terminal_pos: Optional[Seque
         # ---- run_diffusion_maps ----
         with dv.stage("knn_total"):
             idx, dist, kstats = dv.knn_like_sklearn(x_dev, min(knn + 1, n), shard=True)
+        order = kstats.pop("perm", None)
         kern = dv.adaptive_kernel(idx, dist, knn, alpha)
+        kern.order = order
         tvals, lam, U = utils._diffusion_maps_device(kern, n_components, dm_seed)
         # ---- determine_multiscale_space (eigen-gap rule on 10 numbers, column scaling) ----
         lam_t = torch.from_numpy(np.ascontiguousarray(lam)).to(U.device)

@@ -56,14 +56,17 @@ def _knn_table(values: np.ndarray, n_neighbors: int):
     x = dv.to_device(values)
     with dv.stage("knn_total"):
         idx, dist, stats = dv.knn_like_sklearn(x, n_neighbors, shard=True)
+    order = stats.pop("perm", None)
     LAST_INFO["knn"] = stats
-    return idx, dist
+    return idx, dist, order
 
 
 def _compute_kernel_device(values: np.ndarray, knn: int, alpha: float) -> dv.DeviceCSR:
     n = values.shape[0]
-    idx, dist = _knn_table(values, min(knn + 1, n))
-    return dv.adaptive_kernel(idx, dist, knn, alpha)
+    idx, dist, order = _knn_table(values, min(knn + 1, n))
+    kern = dv.adaptive_kernel(idx, dist, knn, alpha)
+    kern.order = order
+    return kern
 
 
 def compute_kernel(data, knn: int = 30, alpha: float = 0, pca_key: str = "X_pca",

@@ -429,6 +429,41 @@ def test_spmv_vs_scipy(pb):
     assert np.max(np.abs(y.cpu().numpy() - k @ x)) <= 1e-12
 
 
+def test_windowed_spmv_and_relabelled_matrix_vs_scipy(pb):
+    """The eigensolver's SpMV on the relabelled matrix (x window in shared memory) against scipy, on a
+    matrix large enough to take the windowed kernel, with columns inside and far outside the window."""
+    import torch
+    from scipy.sparse import coo_matrix
+    from palantir_b200 import _device as dv
+
+    rng = np.random.default_rng(11)
+    n, per_row = 150_000, 24
+    rows = np.repeat(np.arange(n), per_row)
+    near = rows + rng.integers(-9000, 9000, rows.size)
+    far = rng.integers(0, n, rows.size)
+    cols = np.where(rng.random(rows.size) < 0.8, near, far) % n
+    a = coo_matrix((rng.normal(size=rows.size), (rows, cols)), shape=(n, n)).tocsr()
+    a.sum_duplicates()
+    x = rng.normal(size=n)
+    indptr, indices, vals = (dv.to_device(a.indptr.astype(np.int32)), dv.to_device(a.indices.astype(np.int32)),
+                             dv.to_device(a.data))
+    y = dv.empty((n,), dv.F64)
+    dv.call("pb200_csr_spmv_window_f64", indptr, indices, vals, n, a.nnz, dv.to_device(x), y)
+    ref = a @ x
+    assert np.max(np.abs(y.cpu().numpy() - ref)) < 1e-11 * np.abs(ref).max()
+    # relabelling: (P A P^T)(P x) = P (A x)
+    perm = rng.permutation(n).astype(np.int32)
+    inv = np.empty(n, np.int32); inv[perm] = np.arange(n, dtype=np.int32)
+    lens = np.diff(a.indptr)[perm]
+    ip = np.zeros(n + 1, np.int32); ip[1:] = np.cumsum(lens)
+    ind_p, val_p = dv.empty((a.nnz,), dv.I32), dv.empty((a.nnz,), dv.F64)
+    dv.call("pb200_csr_permute", indptr, indices, vals, n, dv.to_device(perm), dv.to_device(inv), dv.to_device(ip),
+            ind_p, val_p)
+    y2 = dv.empty((n,), dv.F64)
+    dv.call("pb200_csr_spmv_window_f64", dv.to_device(ip), ind_p, val_p, n, a.nnz, dv.to_device(x[perm]), y2)
+    assert np.max(np.abs(y2.cpu().numpy() - ref[perm])) < 1e-11 * np.abs(ref).max()
+
+
 def test_magic_imputation_vs_oracle(pb, po):
     z = golden("dm_f64_n600_d8.npz")
     res = pb.utils.run_diffusion_maps(pd.DataFrame(z["x"]), kernel_backend="sklearn")
