@@ -47,6 +47,11 @@ dc.SSSP_MODE = "csr"; lib.pb200_sssp_set_variant(4)
 Dref = run("csr v4 (128 thr)")
 if "--one" in sys.argv:
     sys.exit(0)
+if "--small-delta" in sys.argv:
+    dc.SSSP_MODE = "csr"; lib.pb200_sssp_set_variant(4)
+    for mult in (1.5, 2.0, 2.5, 3.0, 4.0, 5.0):
+        run("csr v4", mult)
+    sys.exit(0)
 if "--delta" in sys.argv:
     dc.SSSP_MODE = "arcrec"; dc.SSSP_THREADS = None
     for ns in (1198, 599, 300, 150):
