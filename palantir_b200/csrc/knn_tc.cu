@@ -72,14 +72,15 @@ struct TcCtl {
   uint64_t a_full;
   uint64_t b_full[8], b_empty[8];
   uint64_t acc_full[TC_NACC], acc_empty[TC_NACC];
-  uint64_t yn_full[TC_NACC];
+  uint64_t yn_full[TC_NACC + 1];
   int tile_ring[16];      // tile ids, producer -> MMA issuer (one entry per tile)
   int acc_tile[TC_NACC];
   int cnt[TC_BM];
   float thr[TC_BM];
   float xcn[TC_BM];
   float warp_bound[4];
-  alignas(16) float yn[TC_NACC][TC_BN];   // bulk-copy destination and float4 reads
+  alignas(16) float yn[TC_NACC + 1][TC_BN];   // bulk-copy destination and float4 reads; one slot more than
+                                              // accumulators: a tile's norms are still read after its accumulator is released
   double qlo[3], qhi[3];
   uint32_t tmem_base;
 };
@@ -152,6 +153,29 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
+}
+
+// the same load without the wait, and the wait (the registers are tied to it so that no use moves above it)
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 
 __device__ __forceinline__ int tc_tile_of(int s, int q, int T) {
@@ -241,7 +265,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
   if (tid == 0) {
     mbar_init(&ctl.a_full, 4);
     for (int s = 0; s < NST; ++s) { mbar_init(&ctl.b_full[s], 1); mbar_init(&ctl.b_empty[s], 1); }
-    for (int b = 0; b < TC_NACC; ++b) { mbar_init(&ctl.acc_full[b], 1); mbar_init(&ctl.acc_empty[b], 4); mbar_init(&ctl.yn_full[b], 1); }
+    for (int b = 0; b < TC_NACC; ++b) { mbar_init(&ctl.acc_full[b], 1); mbar_init(&ctl.acc_empty[b], 4); }
+    for (int b = 0; b <= TC_NACC; ++b) mbar_init(&ctl.yn_full[b], 1);
     fence_mbar_init();
     if (p.box_lo) {
       for (int a = 0; a < 3; ++a) { ctl.qlo[a] = p.box_lo[(long long)qtile * 3 + a]; ctl.qhi[a] = p.box_hi[(long long)qtile * 3 + a]; }
@@ -351,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       mbar_wait(&ctl.a_full, 0);                 // query operand stored to TMEM by the epilogue warps
       tc_fence_after();
       const uint64_t b_desc0 = tc_smem_desc(smem_u32(b_smem));
-      int st = 0, tslot = 0, buf = 0;
+      int st = 0, tslot = 0, buf = 0, ys = 0;
       uint32_t ph = 0, accph = 0;
       for (;;) {
         // ---- one reference tile: KCH ring stages into accumulator `buf` ----
@@ -367,8 +392,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
           break;
         }
         // reference norms of this tile for the epilogue
-        mbar_arrive_expect_tx(&ctl.yn_full[buf], TC_BN * 4);
-        bulk_g2s(&ctl.yn[buf][0], p.yn + (long long)tile * TC_BN, TC_BN * 4, &ctl.yn_full[buf]);
+        mbar_arrive_expect_tx(&ctl.yn_full[ys], TC_BN * 4);
+        bulk_g2s(&ctl.yn[ys][0], p.yn + (long long)tile * TC_BN, TC_BN * 4, &ctl.yn_full[ys]);
+        if (++ys > NACC) ys = 0;
         const uint32_t d_tmem = tmem + (uint32_t)buf * TC_BN;
         uint32_t a_hi = tmem + acol_hi, a_lo = tmem + acol_lo;
         for (int kc = 0; kc < KCH; ++kc) {
@@ -423,10 +449,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl.a_full);
     }
-    int buf = -1;
-    uint32_t accph = 1;
+    int buf = -1, ys = -1;
+    uint32_t accph = 1, yph = 1;
     for (;;) {
       if (++buf == NACC || buf == 0) { buf = 0; accph ^= 1u; }
+      if (++ys > NACC || ys == 0) { ys = 0; yph ^= 1u; }
       // the next accumulator is not ready: use the time to compact this warp's fuller rows (tighter
       // thresholds earlier, and no bursts of compactions on the critical path later)
       while (!__all_sync(0xffffffffu, mbar_test(&ctl.acc_full[buf], accph))) {
@@ -440,7 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       tc_fence_after();
       const int tile = ctl.acc_tile[buf];
       if (tile < 0) break;
-      mbar_wait(&ctl.yn_full[buf], accph);
+      mbar_wait(&ctl.yn_full[ys], yph);
       const int colbase = tile * TC_BN;
       if (p.debug == 1) {
         tc_fence_before();
@@ -448,15 +475,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         if (lane == 0) mbar_arrive(&ctl.acc_empty[buf]);
         continue;
       }
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
-        uint32_t v[32];
-        tc_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN + cb * 32), v);
-        float thr = ctl.thr[row];
+      // The four 32-column blocks of the tile, software pipelined: the tcgen05.ld of block cb+1 is in
+      // flight while block cb is processed, and the accumulator is handed back to the MMA issuer as
+      // soon as the last block sits in registers, before it is processed.
+      float thr = ctl.thr[row];
+      const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN);
+      auto process = [&](uint32_t (&v)[32], const int cb) {
         float q[8];                                  // minimum of each group of four columns
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 y = *reinterpret_cast<const float4*>(&ctl.yn[buf][cb * 32 + j4 * 4]);
+          const float4 y = *reinterpret_cast<const float4*>(&ctl.yn[ys][cb * 32 + j4 * 4]);
           const float s0 = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 0]), y.x);
           const float s1 = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 1]), y.y);
           const float s2 = fmaf(-2.f, __uint_as_float(v[j4 * 4 + 2]), y.z);
@@ -500,10 +528,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
           }
           ctl.cnt[row] = c;
         }
+      };
+      {
+        uint32_t va[32], vb[32];
+        tc_ld32_issue(tbase, va);
+#pragma unroll 1
+        for (int pair = 0; pair < 2; ++pair) {
+          tc_ld32_wait(va);
+          tc_ld32_issue(tbase + (uint32_t)(pair * 64 + 32), vb);
+          process(va, pair * 2);
+          tc_ld32_wait(vb);
+          if (pair == 0) {
+            tc_ld32_issue(tbase + 64u, va);
+          } else {
+            // every column of this accumulator has been read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl.acc_empty[buf]);
+          }
+          process(vb, pair * 2 + 1);
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl.acc_empty[buf]);
       if (__any_sync(0xffffffffu, compacted_any)) {
         float b = ctl.xcn[row] != -INFINITY ? __fadd_ru(ctl.thr[row], ctl.xcn[row]) : -INFINITY;
 #pragma unroll
@@ -651,6 +696,7 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   p.d8 = d8;
   p.nacc = (512 - 2 * d8) / TC_BN;
   if (p.nacc > TC_NACC) p.nacc = TC_NACC;
+  { const char* e = getenv("PB200_TC_NACC"); if (e && atoi(e) >= 1 && atoi(e) < p.nacc) p.nacc = atoi(e); }   // dev: fewer accumulators
   int nst = TC_NST;
   { const char* e = getenv("PB200_TC_NST"); if (e && atoi(e) >= 2 && atoi(e) < nst) nst = atoi(e); }
   p.nst = nst;
