@@ -159,6 +159,8 @@ def unpermute_rows(a: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
     n = a.shape[0]
     m = 1 if a.dim() == 1 else a.shape[1]
     out = torch.empty_like(a)
+    if n == 0 or m == 0:                       # e.g. fate probabilities when no terminal state was found
+        return out
     call("pb200_unpermute_rows_f64", a.contiguous(), n, m, perm, out)
     return out
 

@@ -19,6 +19,7 @@ import numpy as np
 import pandas as pd
 import torch
 
+from . import _devcache
 from . import _device as dv
 from . import _device_core as dc
 from . import _dist, config
@@ -228,7 +229,9 @@ def run_palantir(data, early_cell, terminal_states=None, knn: int = 30, num_wayp
     index = ms_data.index
     n = len(index)
     ms_vals = ms_data.values
-    ms_dev = dv.to_device(ms_vals if ms_vals.dtype == np.float64 else ms_vals.astype(np.float64))
+    ms_dev = _devcache.lookup(ms_vals)             # still on the device from determine_multiscale_space?
+    if ms_dev is None or ms_dev.shape != ms_vals.shape or ms_dev.dtype != torch.float64:
+        ms_dev = dv.to_device(ms_vals if ms_vals.dtype == np.float64 else ms_vals.astype(np.float64))
     dev = dc.minmax_scale(ms_dev) if scale_components else ms_dev.clone()
 
     # boundary cells and the start cell (core.py:186-192)

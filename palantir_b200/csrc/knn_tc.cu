@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
     const int row = quarter * 32 + lane;           // CTA-local query row owned by this thread
     unsigned long long* mybuf = lists + row * TC_LSTRIDE;
     bool compacted_any = false;
+    int c = 0;                                     // entries in this row's buffer (shared copy written before compactions)
     {
       // this thread's query row -> TMEM lane `row`: hi coordinates at columns acol_hi.., lo at acol_lo..
       const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16);
@@ -457,10 +458,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       // the next accumulator is not ready: use the time to compact this warp's fuller rows (tighter
       // thresholds earlier, and no bursts of compactions on the critical path later)
       while (!__all_sync(0xffffffffu, mbar_test(&ctl.acc_full[buf], accph))) {
-        const unsigned fuller = __ballot_sync(0xffffffffu, ctl.cnt[row] > p.k_keep + TC_IDLE_MARGIN);
+        const unsigned fuller = __ballot_sync(0xffffffffu, c > p.k_keep + TC_IDLE_MARGIN);
         if (!fuller) break;
         const int l = __ffs(fuller) - 1;
+        ctl.cnt[row] = c;
+        __syncwarp();
         tc_compact_row(&ctl, lists + (quarter * 32 + l) * TC_LSTRIDE, quarter * 32 + l, p.k_keep, lane);
+        c = ctl.cnt[row];
         compacted_any = true;
       }
       mbar_wait(&ctl.acc_full[buf], accph);
@@ -496,9 +500,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         const float m = fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])), fminf(fminf(q[4], q[5]), fminf(q[6], q[7])));
         if (__any_sync(0xffffffffu, m < thr) && p.debug != 2) {
           // room for this step's (at most 32) pushes: rows above TC_HIGH are compacted first
-          int c = ctl.cnt[row];
           const unsigned need = __ballot_sync(0xffffffffu, c > TC_HIGH);
           if (need) {
+            ctl.cnt[row] = c;
             __syncwarp();
             for (unsigned mm = need; mm; mm &= mm - 1) {
               const int l = __ffs(mm) - 1;
@@ -526,7 +530,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
               }
             }
           }
-          ctl.cnt[row] = c;
         }
       };
       {
@@ -558,6 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       }
     }
     // ---- emit: final sort of each row of this warp ----
+    ctl.cnt[row] = c;
     __syncwarp();
     for (int l = 0; l < 32; ++l) {
       const int r = quarter * 32 + l;

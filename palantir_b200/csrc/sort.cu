@@ -209,12 +209,14 @@ int pb200_tile_boxes(const double* proj, const int* perm, long long n, long long
 }
 
 int pb200_permute_rows_f64(const double* a, long long n, int m, const int* perm, double* out, void* stream) {
+  if (n <= 0 || m <= 0) return 0;
   permute_rows_kernel<<<div_up(n * m, 256), 256, 0, (cudaStream_t)stream>>>(a, n, m, perm, out);
   PB_CHECK_LAUNCH("permute_rows_kernel");
   return 0;
 }
 
 int pb200_unpermute_rows_f64(const double* a, long long n, int m, const int* perm, double* out, void* stream) {
+  if (n <= 0 || m <= 0) return 0;
   unpermute_rows_kernel<<<div_up(n * m, 256), 256, 0, (cudaStream_t)stream>>>(a, n, m, perm, out);
   PB_CHECK_LAUNCH("unpermute_rows_kernel");
   return 0;

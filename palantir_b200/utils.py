@@ -16,6 +16,7 @@ import pandas as pd
 import torch
 from scipy.sparse import csr_matrix, issparse
 
+from . import _devcache
 from . import _device as dv
 from . import config as palantir_config
 from .compat import is_anndata
@@ -122,6 +123,13 @@ def _diffusion_maps_device(kern: dv.DeviceCSR, n_components: int, seed, t_home: 
     return tvals, lam, U
 
 
+def _eigenvector_frame(U: torch.Tensor) -> pd.DataFrame:
+    """Host DataFrame of the eigenvectors; the device original is remembered for determine_multiscale_space."""
+    host = dv.to_host(U)
+    _devcache.remember(host, U)
+    return pd.DataFrame(host, copy=False)
+
+
 def diffusion_maps_from_kernel(kernel: csr_matrix, n_components: int = 10,
                                seed: Union[int, None] = 0) -> Dict[str, object]:
     """Diffusion map of a kernel matrix (reference utils.py:454-495): returns
@@ -134,7 +142,7 @@ def diffusion_maps_from_kernel(kernel: csr_matrix, n_components: int = 10,
         kern = dv.csr_from_host(kernel)
     tvals, lam, U = _diffusion_maps_device(kern, n_components, seed)
     T = dv.csr_to_host(kern, tvals)
-    return {"T": T, "EigenVectors": pd.DataFrame(dv.to_host(U), copy=False), "EigenValues": pd.Series(lam)}
+    return {"T": T, "EigenVectors": _eigenvector_frame(U), "EigenValues": pd.Series(lam)}
 
 
 def run_diffusion_maps(data, n_components: int = 10, knn: int = 30, alpha: float = 0,
@@ -161,7 +169,7 @@ def run_diffusion_maps(data, n_components: int = 10, knn: int = 30, alpha: float
         k_home = dv.csr_to_host_async(kern)
         t_home: list = []
         tvals, lam, U = _diffusion_maps_device(kern, n_components, seed, t_home)
-        vecs = pd.DataFrame(dv.to_host(U), copy=False)
+        vecs = _eigenvector_frame(U)
         kernel = k_home()
         _remember_device_copy(kernel, kern)
         res = {"T": t_home[0](), "EigenVectors": vecs, "EigenValues": pd.Series(lam)}
@@ -208,9 +216,18 @@ def determine_multiscale_space(dm_res, n_eigs: Union[int, None] = None, eigval_k
             n_eigs = 3
     n_eigs = int(n_eigs)
     ev = np.ravel(np.asarray(d["EigenValues"]))[1:n_eigs]
-    # columns 1..n_eigs-1 (utils.py:905-908); a slice, so the product is the only pass over the data
-    out = pd.DataFrame(d["EigenVectors"].values[:, 1:n_eigs] * (ev / (1 - ev)), index=d["EigenVectors"].index,
-                       copy=False)
+    vecs = d["EigenVectors"].values
+    u_dev = _devcache.lookup(vecs)
+    if u_dev is not None and u_dev.shape == vecs.shape:
+        # the eigenvectors are still on the device (and unchanged on the host): same IEEE products there
+        scale = torch.from_numpy(np.ascontiguousarray(ev / (1 - ev))).to(u_dev.device)
+        ms_dev = (u_dev[:, 1:n_eigs] * scale).contiguous()
+        ms_host = dv.to_host(ms_dev)
+        _devcache.remember(ms_host, ms_dev)
+        out = pd.DataFrame(ms_host, index=d["EigenVectors"].index, copy=False)
+    else:
+        # columns 1..n_eigs-1 (utils.py:905-908); a slice, so the product is the only pass over the data
+        out = pd.DataFrame(vecs[:, 1:n_eigs] * (ev / (1 - ev)), index=d["EigenVectors"].index, copy=False)
     if is_anndata(dm_res):
         dm_res.obsm[out_key] = out.values
     return out

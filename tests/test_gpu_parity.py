@@ -191,6 +191,36 @@ def test_kernel_edited_in_place_is_uploaded_again(pb):
     assert abs(got["T"] - want["T"]).max() < 1e-15
 
 
+def test_device_copies_are_equivalent_and_never_stale(pb):
+    """Results handed from call to call keep a device copy (palantir_b200/_devcache.py); using it must give
+    the same numbers as the host arrays, and an array edited in place must not be served from the copy."""
+    from palantir_b200 import _devcache
+
+    z = golden("dm_f64_n800_d24.npz")
+    res = pb.utils.run_diffusion_maps(pd.DataFrame(z["x"]), knn=int(z["knn"]), kernel_backend="sklearn")
+    assert _devcache.lookup(res["EigenVectors"].values) is not None
+    ms_fast = pb.utils.determine_multiscale_space(res)
+    plain = {"EigenValues": res["EigenValues"].copy(), "EigenVectors": pd.DataFrame(res["EigenVectors"].values.copy())}
+    assert _devcache.lookup(plain["EigenVectors"].values) is None
+    ms_host = pb.utils.determine_multiscale_space(plain)
+    assert np.array_equal(ms_fast.values, ms_host.values)
+    # downstream: run_palantir from the cached multiscale matrix == from a plain copy of it
+    early = ms_fast.index[int(z["early"])]
+    a = pb.core.run_palantir(ms_fast, early, num_waypoints=100, knn=20)
+    b = pb.core.run_palantir(pd.DataFrame(ms_fast.values.copy(), index=ms_fast.index), early, num_waypoints=100, knn=20)
+    assert np.array_equal(a.pseudotime.values, b.pseudotime.values)
+    assert np.array_equal(a.branch_probs.values, b.branch_probs.values)
+    # in-place edit of the eigenvectors: the stale device copy must not be used
+    vals = res["EigenVectors"].values
+    if not vals.flags.writeable:
+        vals = res["EigenVectors"]._mgr.blocks[0].values.T if hasattr(res["EigenVectors"], "_mgr") else vals
+    if vals.flags.writeable:
+        vals[:, 1] *= -1.0
+        ms_edit = pb.utils.determine_multiscale_space(res)
+        assert np.array_equal(ms_edit.values[:, 0], -ms_fast.values[:, 0])
+        assert np.array_equal(ms_edit.values[:, 1:], ms_fast.values[:, 1:])
+
+
 def test_run_diffusion_maps_anndata_keys(pb):
     from palantir_b200.compat import AnnDataLike
 
