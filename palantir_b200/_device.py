@@ -401,6 +401,7 @@ class DeviceCSR:
     data: torch.Tensor      # f64 [nnz]
     n: int
     order: Optional[torch.Tensor] = None    # int32 [n]: a locality-preserving order of the rows (order[i] = row at position i)
+    symmetric: bool = False                 # built here as W + W^T (and scaled symmetrically): no need to check
 
     @property
     def nnz(self) -> int:
@@ -451,6 +452,7 @@ def adaptive_kernel(idx: torch.Tensor, dist: torch.Tensor, knn: int, alpha: floa
             out = empty((kern.nnz,), F64)
             call("pb200_csr_scale", kern.indptr, kern.indices, kern.data, n, deg, deg, out)
             kern = DeviceCSR(kern.indptr, kern.indices, out, n)
+    kern.symmetric = True       # w_ij + w_ji is computed once per pair; D^-a K D^-a scales both mirror entries alike
     return kern
 
 

@@ -104,7 +104,7 @@ def _diffusion_maps_device(kern: dv.DeviceCSR, n_components: int, seed, t_home: 
     """(T values, eigenvalues, eigenvectors) on the device.  With ``t_home`` (a list) the copy of T
     to the host is started before the eigensolver and its finisher appended to the list."""
     n = kern.n
-    if not dv.check_symmetric(kern):
+    if not kern.symmetric and not dv.check_symmetric(kern):
         raise dv.NotSymmetricError(
             "diffusion_maps_from_kernel on B200 runs a symmetric Lanczos solver and needs a symmetric "
             "kernel (compute_kernel always produces one)")
