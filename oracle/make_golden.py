@@ -119,6 +119,39 @@ def case_tiny(core, utils):
                         evals_asis=res["EigenValues"].values)
 
 
+def case_wrappers(core, utils, ms, info, names):
+    """early_cell / find_terminal_states / fallback_terminal_cell of the reference (utils.py:944-1137) on
+    the multiscale matrix of the palantir case, with the generator's components as cell types."""
+    ad = utils.AnnData()
+    labels = np.array(["trunk", "B0", "B1", "B2"])[info["component"]]
+    ad.obs = pd.DataFrame({"celltype": labels}, index=names)
+    ad.obs_names = names
+    ad.obsm = {"DM_EigenVectors_multiscaled": ms.values}
+    ad.obsp, ad.uns = {}, {}
+    found = {}
+    for ct in ("trunk", "B0", "B1", "B2"):
+        try:
+            found[ct] = utils.early_cell(ad, ct)
+        except utils.CellNotFoundException:
+            found[ct] = ""
+    ts = utils.find_terminal_states(ad, ["B0", "B1", "B2", "trunk"])
+    # a cell type that is at no extreme: the middle third of the trunk
+    mid = (info["component"] == 0) & (info["time"] > 0.4) & (info["time"] < 0.6)
+    labels2 = labels.copy(); labels2[mid] = "mid"
+    ad.obs = pd.DataFrame({"celltype": labels2}, index=names)
+    try:
+        utils.early_cell(ad, "mid")
+        mid_found = True
+    except utils.CellNotFoundException:
+        mid_found = False
+    fb = utils.early_cell(ad, "mid", fallback_seed=7)
+    np.savez_compressed(os.path.join(OUT, "wrappers_n1500.npz"), ms=ms.values, labels=labels, labels_mid=labels2,
+                        early=np.array([found[c] for c in ("trunk", "B0", "B1", "B2")]),
+                        ts_cells=np.asarray(ts.index, dtype=str), ts_types=np.asarray(ts.values, dtype=str),
+                        mid_found=mid_found, mid_fallback=str(fb))
+    print("wrappers:", found, dict(ts), "mid found directly:", mid_found, "fallback:", fb)
+
+
 def main():
     warnings.simplefilter("ignore")
     os.makedirs(OUT, exist_ok=True)
@@ -126,6 +159,7 @@ def main():
     _, utils_tight = ref_shim.load_reference(eig_tol=1e-12)
     x, info, names, ms = case_diffusion(core, utils, utils_tight, "dm_f32_n1500_d20", 1500, 20, np.float32)
     case_palantir(core, "palantir_n1500_wp200", ms, info, names, 200)
+    case_wrappers(core, utils, ms, info, names)
     case_diffusion(core, utils, utils_tight, "dm_f64_n600_d8", 600, 8, np.float64)   # d <= 15: kd-tree distances
     case_diffusion(core, utils, utils_tight, "dm_f64_n800_d24", 800, 24, np.float64)  # f64 brute
     case_reference_known_answers(core)

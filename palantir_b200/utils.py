@@ -22,7 +22,12 @@ from . import config as palantir_config
 from .compat import is_anndata
 
 __all__ = ["compute_kernel", "diffusion_maps_from_kernel", "run_diffusion_maps",
-           "determine_multiscale_space", "run_magic_imputation"]
+           "determine_multiscale_space", "run_magic_imputation", "early_cell", "fallback_terminal_cell",
+           "find_terminal_states", "CellNotFoundException"]
+
+
+class CellNotFoundException(Exception):
+    """No cell could be determined by the method used (reference utils.py:23)."""
 
 # last-call diagnostics (kNN flagged rows, Lanczos steps ...) for the bench / tests
 LAST_INFO: dict = {}
@@ -285,3 +290,104 @@ def run_magic_imputation(data, dm_res: Union[dict, None] = None, n_steps: int = 
         dense_out = imputed.todense() if issparse(imputed) else imputed
         imputed = pd.DataFrame(dense_out, index=data.index, columns=data.columns)
     return imputed
+
+
+# ---------------------------------------------------------------------------
+# start / terminal cell helpers (reference utils.py:914-1137): thin callers of the path
+# ---------------------------------------------------------------------------
+def _column_extremes(eigenvectors: np.ndarray):
+    """(argmax, argmin) position of every column, first occurrence like numpy's argmax / argmin;
+    one device pass over the matrix (its device original is used when it is still there)."""
+    dev = _devcache.lookup(eigenvectors)
+    if dev is None or dev.dtype != torch.float64 or dev.shape != eigenvectors.shape:
+        vals = eigenvectors if eigenvectors.dtype == np.float64 else eigenvectors.astype(np.float64)
+        dev = dv.to_device(vals)
+    from . import _device_core as dc
+
+    _, imin, _, imax = dc.col_minmax(dev)
+    return imax.cpu().numpy(), imin.cpu().numpy()
+
+
+def early_cell(ad, celltype: str, celltype_column: str = "celltype",
+               eigvec_key: str = "DM_EigenVectors_multiscaled", fallback_seed: Optional[int] = None):
+    """The cell of ``celltype`` sitting at an extreme of a diffusion component (reference
+    utils.py:944-1031): components are tried in order, maximum before minimum; with
+    ``fallback_seed`` the reverse-pseudotime search of ``fallback_terminal_cell`` is used when no
+    component qualifies, otherwise ``CellNotFoundException`` is raised."""
+    if not is_anndata(ad):
+        raise ValueError("'ad' should be an instance of AnnData")
+    if eigvec_key not in ad.obsm:
+        raise ValueError(
+            f"'{eigvec_key}' not found in ad.obsm. "
+            "Run `palantir.utils.run_diffusion_maps(ad)` to "
+            "compute diffusion map eigenvectors.")
+    eigenvectors = ad.obsm[eigvec_key]
+    if isinstance(eigenvectors, pd.DataFrame):
+        eigenvectors = eigenvectors.values
+    if not isinstance(celltype_column, str):
+        raise ValueError(f"celltype_column='{celltype_column}' should be a string")
+    if celltype_column not in ad.obs.columns:
+        raise ValueError(f"celltype_column='{celltype_column}' should be a column of ad.obs.")
+    if not isinstance(celltype, str):
+        raise ValueError("celltype should be a string")
+    labels = ad.obs[celltype_column]
+    if celltype not in labels.values:
+        raise ValueError(f"Celltype '{celltype}' not found in ad.obs['{celltype_column}'].")
+    if fallback_seed is not None and not isinstance(fallback_seed, int):
+        raise ValueError("'fallback_seed' should be an integer")
+
+    imax, imin = _column_extremes(np.asarray(eigenvectors))
+    for dcomp in range(eigenvectors.shape[1]):
+        for pos, which in ((int(imax[dcomp]), "max"), (int(imin[dcomp]), "min")):
+            if labels.iloc[pos] == celltype:
+                cell = ad.obs_names[pos]
+                print(f"Using {cell} for cell type {celltype} which is {which} in "
+                      f"diffusion component {dcomp}.")
+                return cell
+    if fallback_seed is not None:
+        print("Falling back to slow early cell detection.")
+        return fallback_terminal_cell(ad, celltype, celltype_column=celltype_column, eigvec_key=eigvec_key,
+                                      seed=fallback_seed)
+    raise CellNotFoundException(
+        f"No valid component found: {celltype} "
+        "Consider increasing the number of diffusion components "
+        "('n_components' in palantir.utils.run_diffusion_maps) "
+        "or specify a 'fallback_seed' to determine an early cell based on "
+        f"reverse pseudotime starting from random non-{celltype} cell.")
+
+
+def fallback_terminal_cell(ad, celltype: str, celltype_column: str = "anno",
+                           eigvec_key: str = "DM_EigenVectors_multiscaled", seed: int = 2353):
+    """Reference utils.py:1034-1083: start Palantir from a random cell of another type (pandas'
+    ``sample(1, random_state=seed)``) and return the cell of ``celltype`` with the largest pseudotime.
+    Like the reference call, this writes the run's results into ``ad``."""
+    from .core import run_palantir
+
+    other_cells = ad.obs_names[ad.obs[celltype_column] != celltype]
+    fake_early_cell = other_cells.to_series().sample(1, random_state=seed).iloc[0]
+    pr_res = run_palantir(ad, fake_early_cell, eigvec_key=eigvec_key, terminal_states=None,
+                          use_early_cell_as_start=True)
+    idx = ad.obs[celltype_column] == celltype
+    ec = pr_res.pseudotime[idx].argmax()
+    cell = ad.obs_names[idx][ec]
+    print(f"Using {cell} for cell type {celltype} which is latest cell in "
+          f"{celltype} when starting from {fake_early_cell}.")
+    return cell
+
+
+def find_terminal_states(ad, celltypes, celltype_column: str = "celltype",
+                         eigvec_key: str = "DM_EigenVectors_multiscaled", fallback_seed: Optional[int] = None):
+    """Reference utils.py:1086-1137: ``early_cell`` for every cell type; types without a qualifying
+    component are skipped with a warning.  Returns a Series cell -> cell type."""
+    terminal_states = pd.Series(dtype=str)
+    for ct in celltypes:
+        try:
+            cell = early_cell(ad, ct, celltype_column, eigvec_key, fallback_seed)
+        except CellNotFoundException:
+            warn(f"No valid component found: {ct} "
+                 "Consider increasing the number of diffusion components "
+                 "('n_components' in palantir.utils.run_diffusion_maps). "
+                 f"The cell type {ct} will be skipped.")
+            continue
+        terminal_states[cell] = ct
+    return terminal_states

@@ -221,6 +221,37 @@ def test_device_copies_are_equivalent_and_never_stale(pb):
         assert np.array_equal(ms_edit.values[:, 1:], ms_fast.values[:, 1:])
 
 
+def _wrapper_adata(pb, labels_key="labels"):
+    from palantir_b200.compat import AnnDataLike
+    from palantir_b200.datasets import synth_names
+
+    z = golden("wrappers_n1500.npz")
+    ad = AnnDataLike(X=np.zeros((1500, 1)), obs_names=synth_names(1500))
+    ad.obs["celltype"] = z[labels_key]
+    ad.obsm["DM_EigenVectors_multiscaled"] = z["ms"]
+    return ad, z
+
+
+def test_early_cell_and_find_terminal_states_match_reference(pb):
+    """utils.py:944-1137 of the reference on the fixture it produced (oracle/make_golden.py::case_wrappers)."""
+    ad, z = _wrapper_adata(pb)
+    for ct, want in zip(("trunk", "B0", "B1", "B2"), z["early"]):
+        assert pb.utils.early_cell(ad, ct) == str(want)
+    ts = pb.utils.find_terminal_states(ad, ["B0", "B1", "B2", "trunk"])
+    assert list(ts.index) == [str(c) for c in z["ts_cells"]] and list(ts.values) == [str(t) for t in z["ts_types"]]
+
+
+def test_early_cell_fallback_matches_reference(pb):
+    ad, z = _wrapper_adata(pb, "labels_mid")
+    with pytest.raises(pb.utils.CellNotFoundException):
+        pb.utils.early_cell(ad, "mid")
+    with pytest.warns(UserWarning, match="will be skipped"):
+        ts = pb.utils.find_terminal_states(ad, ["mid", "B0"])
+    assert list(ts.values) == ["B0"]
+    assert pb.utils.early_cell(ad, "mid", fallback_seed=7) == str(z["mid_fallback"])
+    assert "palantir_pseudotime" in ad.obs.columns          # the fallback run writes into `ad`, as the reference's does
+
+
 def test_run_diffusion_maps_anndata_keys(pb):
     from palantir_b200.compat import AnnDataLike
 

@@ -189,3 +189,29 @@ def test_sharding_world_size_2_gloo(tmp_path):
         out, err = p.communicate(timeout=180)
         assert p.returncode == 0, err
         assert "ok" in out
+
+
+def test_early_cell_argument_checks_match_the_reference():
+    """The ValueErrors of utils.py:979-1011 are raised before any device work."""
+    import pandas as pd
+    import pytest
+    from palantir_b200 import utils
+    from palantir_b200.compat import AnnDataLike
+
+    ad = AnnDataLike(X=np.zeros((4, 1)))
+    ad.obs["celltype"] = ["a", "a", "b", "b"]
+    with pytest.raises(ValueError, match="should be an instance of AnnData"):
+        utils.early_cell(pd.DataFrame(np.zeros((4, 2))), "a")
+    with pytest.raises(ValueError, match="not found in ad.obsm"):
+        utils.early_cell(ad, "a")
+    ad.obsm["DM_EigenVectors_multiscaled"] = np.zeros((4, 2))
+    with pytest.raises(ValueError, match="should be a column of ad.obs"):
+        utils.early_cell(ad, "a", celltype_column="nope")
+    with pytest.raises(ValueError, match="should be a string"):
+        utils.early_cell(ad, "a", celltype_column=3)
+    with pytest.raises(ValueError, match="celltype should be a string"):
+        utils.early_cell(ad, 1)
+    with pytest.raises(ValueError, match="not found in ad.obs"):
+        utils.early_cell(ad, "c")
+    with pytest.raises(ValueError, match="'fallback_seed' should be an integer"):
+        utils.early_cell(ad, "a", fallback_seed=1.5)
