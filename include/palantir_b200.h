@@ -159,6 +159,9 @@ int pb200_csr_spmv_f64(const int* indptr, const int* indices, const double* vals
                        const double* x, double* y, void* stream);
 int pb200_csr_spmm_f32(const int* indptr, const int* indices, const double* vals, long long n, const float* x,
                        long long ldx, float* y, long long ldy, int g, void* stream);
+int pb200_spmv_long_row(void);
+int pb200_csr_spmv_split_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                             const int* long_rows, int n_long, const double* x, double* y, void* stream);
 int pb200_csr_spmv_window_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
                               const double* x, double* y, void* stream);
 /* relabelled copy: row r' = row perm[r'], columns mapped through inv (inv[perm[i]] = i); indptr_new = prefix sums
@@ -172,12 +175,15 @@ int pb200_lanczos_init(const double* w, long long n, double* V0, float* V32_0, d
 /* Lanczos steps j0..j0+nsteps-1 with full re-orthogonalisation (three-term recurrence + one Gram-Schmidt pass); alpha[j], beta[j+1], V[j+1] written.
  * V32 (optional, leading dimension ldv): FP32 shadow of the basis, maintained here and read by the Gram-Schmidt pass
  * (it only removes round-off-level components); NULL = the pass reads the FP64 basis.
+ * long_rows / n_long (optional): the rows above pb200_spmv_long_row() entries (hubs of the symmetrised kNN graph);
+ * the SpMV walks each of them with a whole warp (pb200_csr_spmv_split_f64).
  * windowed != 0: rows are in a locality-preserving order (pb200_csr_permute with the kNN stage's Morton order) and
  * the SpMV keeps the x window of each row block in shared memory (pb200_csr_spmv_window_f64).
  * scratch: w[n], h[j0+nsteps], partial[(j0+nsteps) * (n/2048+1)], tmp[1] */
 int pb200_lanczos_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
-                        double* V, long long ldv, float* V32, int windowed, int j0, int nsteps, double* alpha,
-                        double* beta, double* w, double* h, double* partial, double* tmp, void* stream);
+                        const int* long_rows, int n_long, double* V, long long ldv, float* V32, int windowed, int j0,
+                        int nsteps, double* alpha, double* beta, double* w, double* h, double* partial, double* tmp,
+                        void* stream);
 /* U[n][kk] = diag(scale) * sum_j V[j][:] Y[j][kk]  (scale may be NULL), kk <= 32 */
 int pb200_ritz_vectors(const double* V, long long ldv, int m, const double* Y, int kk, const double* scale,
                        double* U, long long n, void* stream);

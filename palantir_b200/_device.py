@@ -544,6 +544,12 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
         # keep the basis under ~40 GB
         max_basis = int(min(n, max(4 * k + 40, min(2048, (40 << 30) // (8 * n)))))
     max_basis = min(max_basis, n)
+    # hub rows of the symmetrised kNN graph: listed once, walked by a whole warp each in every SpMV
+    lens = indptr[1:] - indptr[:-1]
+    long_rows = torch.nonzero(lens > int(_native.load().pb200_spmv_long_row())).to(I32).reshape(-1).contiguous()
+    n_long = int(long_rows.numel())
+    if n_long == 0:
+        long_rows = None
     ld = n
     nblk = n // 2048 + 1
     V = empty((max_basis + 1, ld), F64)
@@ -561,7 +567,8 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
     while m < max_basis:
         steps = min(batch, max_basis - m)
         with stage("lanczos_steps"):
-            call("pb200_lanczos_steps", indptr, indices, svals, n, nnz, V, ld, V32, int(perm is not None and SPMV_WINDOW_KERNEL), m, steps,
+            call("pb200_lanczos_steps", indptr, indices, svals, n, nnz, long_rows, n_long, V, ld, V32,
+                 int(perm is not None and SPMV_WINDOW_KERNEL), m, steps,
                  alpha, beta, w, h, partial, tmp)
         m += steps
         if m < k + 1 and m < max_basis:

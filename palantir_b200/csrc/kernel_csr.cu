@@ -166,7 +166,8 @@ __global__ void scatter_arcs_kernel(const int* __restrict__ idx, const double* _
 }
 
 constexpr int SYM_WARPS = 4;
-constexpr int SYM_CAP = 768;  // bucket entries sorted through shared memory per warp
+constexpr int SYM_CAP = 192;  // bucket entries sorted through shared memory per warp (12 KB per block: full occupancy);
+                              // longer rows are sorted in place in global memory
 
 // mode 0: sum duplicates (W + W^T); mode 1: min (undirected shortest-path graph).
 __global__ void __launch_bounds__(SYM_WARPS * 32) merge_rows_kernel(long long n, const long long* __restrict__ off,
@@ -215,26 +216,50 @@ __global__ void __launch_bounds__(SYM_WARPS * 32) merge_rows_kernel(long long n,
     }
     if (lane == 0) row_nnz[row] = base;
   } else {
-    // rare hub rows: rank directly in global memory, output through the second half trick is
-    // impossible in place, so do a serial insertion sort by lane 0 (correct, slow, rare).
-    if (lane == 0) {
-      for (int e = 1; e < len; ++e) {
-        const int c = tcol[b + e];
-        const double v = tval[b + e];
-        int f = e - 1;
-        while (f >= 0 && tcol[b + f] > c) { tcol[b + f + 1] = tcol[b + f]; tval[b + f + 1] = tval[b + f]; --f; }
-        tcol[b + f + 1] = c; tval[b + f + 1] = v;
-      }
-      int o = 0;
-      for (int e = 0; e < len; ++e) {
-        if (o > 0 && tcol[b + o - 1] == tcol[b + e]) {
-          tval[b + o - 1] = mode == 0 ? tval[b + o - 1] + tval[b + e] : fmin(tval[b + o - 1], tval[b + e]);
-        } else {
-          tcol[b + o] = tcol[b + e]; tval[b + o] = tval[b + e]; ++o;
+    // hub rows (the symmetrised kNN graph of noisy high-dimensional data has them: 1283 rows above 768
+    // entries, the longest 3948, at 1 M cells): warp-parallel bitonic sort IN PLACE in global memory, in
+    // the formulation whose compare-exchanges all put the smaller key at the lower index (first step of
+    // every merge pairs i with i ^ (2k-1)), so the virtual +inf padding beyond len never moves.
+    int np2 = 1;
+    while (np2 < len) np2 <<= 1;
+    for (int k = 2; k <= np2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const int mask = (j == (k >> 1)) ? (k - 1) : j;
+        for (int i = lane; i < np2; i += 32) {
+          const int pj = i ^ mask;
+          if (pj > i && pj < len) {
+            const int ci = tcol[b + i], cj = tcol[b + pj];
+            if (cj < ci) {
+              const double vi = tval[b + i], vj = tval[b + pj];
+              tcol[b + i] = cj; tcol[b + pj] = ci;
+              tval[b + i] = vj; tval[b + pj] = vi;
+            }
+          }
         }
+        __syncwarp();
       }
-      row_nnz[row] = o;
     }
+    // merge equal neighbours in place: heads are written at or below their own position, one 32-entry
+    // chunk after the other, every lane having read its inputs before any lane of the chunk writes
+    int base = 0;
+    for (int e0 = 0; e0 < len; e0 += 32) {
+      const int e = e0 + lane;
+      const bool valid = e < len;
+      const int c = valid ? tcol[b + e] : 0;
+      const bool head = valid && (e == 0 || tcol[b + e - 1] != c);
+      double v = valid ? tval[b + e] : 0.0;
+      if (head && e + 1 < len && tcol[b + e + 1] == c) v = mode == 0 ? v + tval[b + e + 1] : fmin(v, tval[b + e + 1]);
+      const unsigned m = __ballot_sync(0xffffffffu, head);
+      __syncwarp();
+      if (head) {
+        const int o = base + __popc(m & ((1u << lane) - 1u));
+        tcol[b + o] = c;
+        tval[b + o] = v;
+      }
+      __syncwarp();
+      base += __popc(m);
+    }
+    if (lane == 0) row_nnz[row] = base;
   }
 }
 

@@ -25,16 +25,19 @@ namespace pb200 {
 // streams are read coalesced, x is gathered through L2.  HBM-bound:
 // 12 B/nnz + 4 B/row (indptr) + 8 B/row (y) + x once.
 // ---------------------------------------------------------------------------
+constexpr int SPMV_LONG_ROW = 128;   // rows above this many entries go to csr_spmv_long_rows_kernel when a list is given
+
 template <int L>
 __global__ void __launch_bounds__(256) csr_spmv_kernel(const int* __restrict__ indptr,
                                                        const int* __restrict__ indices,
                                                        const double* __restrict__ vals,
                                                        const double* __restrict__ x, double* __restrict__ y,
-                                                       long long n) {
+                                                       long long n, int skip_long) {
   const int lane = threadIdx.x & (L - 1);
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
   if (row >= n) return;  // whole sub-warp leaves together
   const int beg = indptr[row], end = indptr[row + 1];
+  if (skip_long && end - beg > SPMV_LONG_ROW) return;
   double s0 = 0.0, s1 = 0.0;
   int e = beg + lane;
   for (; e + L < end; e += 2 * L) {
@@ -190,6 +193,36 @@ __global__ void __launch_bounds__(256) csr_permute_kernel(const int* __restrict_
     indices_new[nb + t] = inv[indices[b + t]];
     vals_new[nb + t] = vals[b + t];
   }
+}
+
+// The long rows of the same product, one warp per row, eight gathers in flight per lane.  The symmetrised
+// kNN graph of noisy high-dimensional data has hubs (longest row 3948 at 1 M cells, 5 % of the rows above
+// 128 entries holding 13 % of the nonzeros): walked by 16 lanes they are a third of the SpMV's time.
+__global__ void __launch_bounds__(256) csr_spmv_long_rows_kernel(const int* __restrict__ indptr,
+                                                                 const int* __restrict__ indices,
+                                                                 const double* __restrict__ vals,
+                                                                 const double* __restrict__ x, double* __restrict__ y,
+                                                                 const int* __restrict__ rows, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (w >= n_rows) return;
+  const int row = rows[w];
+  const int beg = indptr[row], end = indptr[row + 1];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int e = beg + lane;
+  for (; e + 96 < end; e += 128) {
+    const int c0 = indices[e], c1 = indices[e + 32], c2 = indices[e + 64], c3 = indices[e + 96];
+    const double v0 = vals[e], v1 = vals[e + 32], v2 = vals[e + 64], v3 = vals[e + 96];
+    s0 = fma(v0, __ldg(x + c0), s0);
+    s1 = fma(v1, __ldg(x + c1), s1);
+    s2 = fma(v2, __ldg(x + c2), s2);
+    s3 = fma(v3, __ldg(x + c3), s3);
+  }
+  for (; e < end; e += 32) s0 = fma(vals[e], __ldg(x + indices[e]), s0);
+  double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[row] = s;
 }
 
 // SpMM for MAGIC: Y[n][g] (+)= A X[n][g], FP32 dense operands, FP64 CSR values
@@ -419,15 +452,23 @@ static int launch_spmv_window(const int* indptr, const int* indices, const doubl
 }
 
 static int launch_spmv(const int* indptr, const int* indices, const double* vals, const double* x, double* y,
-                       long long n, long long nnz, cudaStream_t st, int windowed = 0) {
+                       long long n, long long nnz, cudaStream_t st, int windowed = 0, const int* long_rows = nullptr,
+                       int n_long = 0) {
   if (windowed && n >= 4 * SW_C) return launch_spmv_window(indptr, indices, vals, x, y, n, st);
   const double mean = n > 0 ? (double)nnz / (double)n : 0.0;
+  const int skip = (long_rows != nullptr && n_long > 0) ? 1 : 0;
+  if (skip) {
+    // the long rows first: they are the longest-running warps
+    csr_spmv_long_rows_kernel<<<div_up((long long)n_long * 32, 256), 256, 0, st>>>(indptr, indices, vals, x, y, long_rows,
+                                                                                 n_long);
+    PB_CHECK_LAUNCH("csr_spmv_long_rows_kernel");
+  }
   if (mean > 24.0) {
-    csr_spmv_kernel<16><<<div_up(n * 16, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n);
+    csr_spmv_kernel<16><<<div_up(n * 16, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n, skip);
   } else if (mean > 12.0) {
-    csr_spmv_kernel<8><<<div_up(n * 8, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n);
+    csr_spmv_kernel<8><<<div_up(n * 8, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n, skip);
   } else {
-    csr_spmv_kernel<4><<<div_up(n * 4, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n);
+    csr_spmv_kernel<4><<<div_up(n * 4, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n, skip);
   }
   PB_CHECK_LAUNCH("csr_spmv_kernel");
   return 0;
@@ -466,6 +507,14 @@ int pb200_csr_permute(const int* indptr, const int* indices, const double* vals,
   return 0;
 }
 
+// y = A x with the rows of more than pb200_spmv_long_row() entries listed in long_rows (int32 [n_long]): those are
+// walked by a whole warp each, the others by the kernel of pb200_csr_spmv_f64.
+int pb200_spmv_long_row(void) { return SPMV_LONG_ROW; }
+int pb200_csr_spmv_split_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                             const int* long_rows, int n_long, const double* x, double* y, void* stream) {
+  return launch_spmv(indptr, indices, vals, x, y, n, nnz, (cudaStream_t)stream, 0, long_rows, n_long);
+}
+
 int pb200_csr_spmm_f32(const int* indptr, const int* indices, const double* vals, long long n, const float* x,
                        long long ldx, float* y, long long ldy, int g, void* stream) {
   csr_spmm_f32_kernel<<<div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, vals, x, y, n, g, ldx, ldy);
@@ -496,16 +545,18 @@ int pb200_lanczos_init(const double* w, long long n, double* V0, float* V32_0, d
 // the Gram-Schmidt pass -- what that pass removes are round-off-level components (|h| <~ 1e-13 after
 // the three-term recurrence), so the 6e-8 relative error of the shadow changes w by < 1e-20 while the
 // pass reads half the bytes.  The recurrence itself, alpha, beta and the Ritz vectors use the FP64 basis.
+// long_rows / n_long (optional): rows above pb200_spmv_long_row() entries, walked by a warp each.
 // windowed != 0: the matrix rows are in a locality-preserving order; use the shared-memory-window SpMV.
 // Scratch: w[n], h[mcap], partial[mcap * div_up(n,2048)], tmp[1].
 int pb200_lanczos_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
-                        double* V, long long ldv, float* V32, int windowed, int j0, int nsteps, double* alpha,
-                        double* beta, double* w, double* h, double* partial, double* tmp, void* stream) {
+                        const int* long_rows, int n_long, double* V, long long ldv, float* V32, int windowed, int j0,
+                        int nsteps, double* alpha, double* beta, double* w, double* h, double* partial, double* tmp,
+                        void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = div_up(n, VCHUNK);
   for (int j = j0; j < j0 + nsteps; ++j) {
     const int m = j + 1;
-    int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st, windowed);
+    int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st, windowed, long_rows, n_long);
     if (rc) return rc;
     // three-term recurrence: alpha_j = v_j . w;  w -= alpha_j v_j + beta_j v_{j-1}
     multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V + (long long)j * ldv, ldv, 1, w, n, partial);

@@ -490,6 +490,29 @@ def test_spmv_vs_scipy(pb):
     assert np.max(np.abs(y.cpu().numpy() - k @ x)) <= 1e-12
 
 
+def test_spmv_with_hub_rows_vs_scipy(pb):
+    """Rows above 128 entries are walked by a whole warp (the symmetrised kNN graph has hubs of thousands)."""
+    from scipy.sparse import random as sprandom, vstack
+    from palantir_b200 import _device as dv, _native
+
+    rng = np.random.default_rng(3)
+    n = 20_000
+    a = sprandom(n, n, density=40 / n, random_state=3, format="lil")
+    for r, ln in ((5, 129), (77, 1000), (n - 1, 5000), (1234, 128)):
+        cols = rng.choice(n, ln, replace=False)
+        a.rows[r] = sorted(cols.tolist()); a.data[r] = rng.normal(size=ln).tolist()
+    a = a.tocsr()
+    x = rng.normal(size=n)
+    lens = np.diff(a.indptr)
+    long_rows = np.flatnonzero(lens > int(_native.load().pb200_spmv_long_row())).astype(np.int32)
+    assert len(long_rows) >= 3 and 1234 not in long_rows
+    y = dv.empty((n,), dv.F64)
+    dv.call("pb200_csr_spmv_split_f64", dv.to_device(a.indptr.astype(np.int32)), dv.to_device(a.indices.astype(np.int32)),
+            dv.to_device(a.data), n, a.nnz, dv.to_device(long_rows), len(long_rows), dv.to_device(x), y)
+    ref = a @ x
+    assert np.max(np.abs(y.cpu().numpy() - ref)) < 1e-12 * max(1.0, np.abs(ref).max())
+
+
 def test_windowed_spmv_and_relabelled_matrix_vs_scipy(pb):
     """The eigensolver's SpMV on the relabelled matrix (x window in shared memory) against scipy, on a
     matrix large enough to take the windowed kernel, with columns inside and far outside the window."""
