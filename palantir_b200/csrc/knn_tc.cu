@@ -17,14 +17,14 @@
 //     one bulk copy each (the global copy is stored directly in the UMMA "K-major, no swizzle"
 //     core-matrix layout: 8 rows x 16 bytes per core matrix, LBO = 2048 B between K-adjacent
 //     core matrices, SBO = 128 B between 8-row groups);
-//   * the 128 x 128 FP32 accumulator lives in TMEM, four deep (4 x 128 columns = the whole TMEM of
-//     the SM: the epilogue's time per tile varies a lot with the number of candidates it has to
-//     keep, and the depth absorbs that) so that the MMAs of the next tiles run while the four
-//     epilogue warps drain tile t with tcgen05.ld
-//     (32 lanes x 32 columns per instruction; lane = query row, so a thread owns one row and
-//     its candidate list);
-//   * warp roles: warp 0 = producer (tile choice with 32 box tests per step + bulk copies),
-//     warp 1 = MMA issuer (one elected lane) and TMEM allocator, warps 2-5 = epilogue.
+//   * the 128 x 128 FP32 accumulators take the TMEM columns the operand leaves (two at d = 100,
+//     up to four for small d), so that the MMAs of the next tile run while the four epilogue warps
+//     drain tile t with software-pipelined tcgen05.ld (32 lanes x 32 columns per instruction; lane =
+//     query row, so a thread owns one row and its candidate buffer, which lives in shared memory);
+//   * warp roles: warp 0 = producer (tile choice two steps ahead with 32 box tests per step, bulk
+//     copies), warp 1 = MMA issuer (one lane chosen with elect.sync, so that the compiler emits the
+//     UTCHMMA / UTCBAR instructions without a loop over the active lanes) and TMEM allocator,
+//     warps 2-5 = epilogue.
 // Supports d <= 128 (the resident operand and two accumulators must fit the 512 TMEM columns);
 // larger d uses the SIMT kernel.
 #include <cstdlib>
@@ -44,7 +44,7 @@ constexpr int TC_HIGH = TC_CAP - 32;     // a row above this is compacted before
 constexpr int TC_IDLE_MARGIN = 20;       // rows with more than k_keep + this many entries are compacted in idle time
 constexpr int TC_NST = 5;         // ring stages (16 KB each); the depth does not matter beyond 3 (measured)
 constexpr int TC_MAX_KEEP = 48;
-constexpr int TC_NACC = 4;        // TMEM accumulators (4 x 128 columns = all 512 columns of the SM)
+constexpr int TC_NACC = 4;        // most TMEM accumulators in flight (what 512 columns minus the operand allow)
 constexpr int TC_THREADS = 192;   // 6 warps
 
 struct TcParams {
@@ -61,7 +61,7 @@ struct TcParams {
   int nacc;               // TMEM accumulators in flight: (512 - 2 d8) / 128, 2..4
   int k_keep;
   int debug;              // dev only (PB200_TC_DEBUG): 1 = epilogue releases accumulators unread, 2 = no candidate pushes
-  unsigned long long* lists;
+  unsigned long long* lists;   // unused (kept for the ABI: the candidate buffers live in shared memory)
   int* out_idx;
   float* out_score;
   float* out_thr;
@@ -94,15 +94,6 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
   // descriptor version 1 (sm_100)
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(2048u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) |
          (1ull << 46);
-}
-
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u)
-      : "memory");
 }
 
 // A operand read from TMEM (lane = row, one 32-bit column per coordinate), B from shared memory
@@ -141,21 +132,8 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-
-// the same load without the wait, and the wait (the registers are tied to it so that no use moves above it)
+// 32 lanes x 32 columns of an accumulator -> registers, issue and wait separately (software pipelining):
+// the registers are tied to the wait so that no use moves above it
 __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
