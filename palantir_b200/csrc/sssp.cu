@@ -302,19 +302,28 @@ __global__ void __launch_bounds__(THREADS) sssp_group_kernel(
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) dv[k] = ok[k] ? __ldcg(dist + vv[k]) : 0.0;
+            // the (rare) updates in three batched levels -- all atomicMin of the four arcs, then all
+            // membership atomicOr, then the queue stores -- so that their L2 round trips overlap
+            // instead of following one another (they were a third of the kernel's stall samples)
+            bool imp[4];
+            double oldv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) imp[k] = ok[k] && nd[k] < dv[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oldv[k] = imp[k] ? atomic_min_pos_f64(dist + vv[k], nd[k]) : 0.0;
+            unsigned int prev[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (ok[k] && nd[k] < dv[k]) {
-                const int v = vv[k];
-                const double old = atomic_min_pos_f64(dist + v, nd[k]);
-                if (nd[k] < old) {
-                  const unsigned int bit = 1u << (v & 31);
-                  if (nd[k] < thr) {
-                    if (!(atomicOr(&bnext[v >> 5], bit) & bit)) qb[atomicAdd(&s_cnt[p ^ 1], 1)] = v;
-                  } else {
-                    if (!(atomicOr(&bfar[v >> 5], bit) & bit)) far[atomicAdd(&s_cnt_far, 1)] = v;
-                  }
-                }
+              imp[k] = imp[k] && nd[k] < oldv[k];
+              const unsigned int bit = 1u << (vv[k] & 31);
+              unsigned int* bm = nd[k] < thr ? bnext : bfar;
+              prev[k] = imp[k] ? (atomicOr(&bm[vv[k] >> 5], bit) & bit) : 1u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (!prev[k]) {
+                if (nd[k] < thr) qb[atomicAdd(&s_cnt[p ^ 1], 1)] = vv[k];
+                else far[atomicAdd(&s_cnt_far, 1)] = vv[k];
               }
             }
           }
@@ -498,23 +507,31 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) dv[k] = ok[k] ? __ldcg(dist + ar[k].v) : 0.0;     // level 2
+            // levels 3-5 batched over the four arcs: every atomicMin, then every membership atomicOr, then the stores
+            bool imp[4];
+            double oldv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) imp[k] = ok[k] && nd[k] < dv[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oldv[k] = imp[k] ? atomic_min_pos_f64(dist + ar[k].v, nd[k]) : 0.0;   // level 3
+            unsigned int prev[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (ok[k] && nd[k] < dv[k]) {
-                const int v = ar[k].v;
-                const double old = atomic_min_pos_f64(dist + v, nd[k]);                     // level 3
-                if (nd[k] < old) {
-                  const unsigned int bit = 1u << (v & 31);
-                  if (nd[k] < thr) {
-                    if (!(atomicOr(&bnext[v >> 5], bit) & bit)) {                           // level 4
-                      qb[atomicAdd(&s_cnt[p ^ 1], 1)] = make_int2(v, ar[k].beg);
-                      const char* row = reinterpret_cast<const char*>(arcs + ar[k].beg);
-                      prefetch_l2(row); prefetch_l2(row + 128); prefetch_l2(row + 256);
-                      prefetch_l2(row + 384); prefetch_l2(row + 512);
-                    }
-                  } else {
-                    if (!(atomicOr(&bfar[v >> 5], bit) & bit)) far[atomicAdd(&s_cnt_far, 1)] = make_int2(v, ar[k].beg);
-                  }
+              imp[k] = imp[k] && nd[k] < oldv[k];
+              const unsigned int bit = 1u << (ar[k].v & 31);
+              unsigned int* bm = nd[k] < thr ? bnext : bfar;
+              prev[k] = imp[k] ? (atomicOr(&bm[ar[k].v >> 5], bit) & bit) : 1u;                             // level 4
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (!prev[k]) {
+                if (nd[k] < thr) {
+                  qb[atomicAdd(&s_cnt[p ^ 1], 1)] = make_int2(ar[k].v, ar[k].beg);
+                  const char* row = reinterpret_cast<const char*>(arcs + ar[k].beg);
+                  prefetch_l2(row); prefetch_l2(row + 128); prefetch_l2(row + 256);
+                  prefetch_l2(row + 384); prefetch_l2(row + 512);
+                } else {
+                  far[atomicAdd(&s_cnt_far, 1)] = make_int2(ar[k].v, ar[k].beg);
                 }
               }
             }

@@ -52,6 +52,13 @@ if "--small-delta" in sys.argv:
     for mult in (1.5, 2.0, 2.5, 3.0, 4.0, 5.0):
         run("csr v4", mult)
     sys.exit(0)
+if "--sources" in sys.argv:
+    dc.SSSP_MODE = "arcrec"; dc.SSSP_THREADS = None
+    for ns in (1198, 599, 300, 150, 1):
+        for mult in (2.5, 4.0):
+            D = run("auto", mult, nsrc=ns)
+        print("   identical to the reference rows:", bool(torch.equal(D, Dref[:ns])))
+    sys.exit(0)
 if "--delta" in sys.argv:
     dc.SSSP_MODE = "arcrec"; dc.SSSP_THREADS = None
     for ns in (1198, 599, 300, 150):
