@@ -201,8 +201,8 @@ def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, 
     """D[S, n] shortest-path distances from each source (unreachable = +inf)."""
     n, S = g.n, int(sources.numel())
     if delta is None:
-        # bucket width: measured 1.5x .. 5x the mean arc weight at 1198 sources / 1 M cells: 480, 477, 475 (2.5x),
-        # 483, 490, 493 ms -- fewer re-relaxations against more threshold advances, a flat optimum
+        # bucket width: measured 2x .. 5x the mean arc weight at 1198 sources / 1 M cells: 393, 390 (2.5x), 397, 403,
+        # 410 ms -- fewer re-relaxations against more threshold advances, a flat optimum
         delta = 2.5 * float(g.data.mean().item()) if g.nnz else 1.0
         if not (delta > 0.0):
             delta = 1.0

@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_flat_kernel(
 // (two block barriers per round).  Distances are re-read when the vertex is expanded, so later
 // vertices of a round see the improvements made by earlier ones (fewer re-relaxations than a
 // snapshot of the whole frontier).
-template <int THREADS, int LPV>
-__global__ void __launch_bounds__(THREADS) sssp_group_kernel(
+template <int THREADS, int LPV, int UNR = 4, int MINB = 0>
+__global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
     const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ wts, int n,
     const long long* __restrict__ sources, int n_sources, double delta, double* __restrict__ D,
     int* __restrict__ q_all, unsigned int* __restrict__ bits_all, long long* __restrict__ stats) {
@@ -284,43 +284,46 @@ __global__ void __launch_bounds__(THREADS) sssp_group_kernel(
         int* qb = qbuf[p ^ 1];
         unsigned int* bcur = bnear[p];
         unsigned int* bnext = bnear[p ^ 1];
+        // (prefetching the next vertex of the group was measured: its id and row extent one vertex ahead
+        // changes nothing, its distance one vertex ahead is stale often enough to raise the re-relaxations
+        // from 1.5 to 1.8 per arc and the time by a quarter)
         for (int i = grp; i < cnt; i += NG) {
           const int u = qa[i];
-          if (sub == 0) atomicAnd(&bcur[u >> 5], ~(1u << (u & 31)));   // popped
           const double du = __ldcg(dist + u);
           const int beg = indptr[u], end = indptr[u + 1];
-          for (int e0 = beg + sub; e0 < end; e0 += 4 * LPV) {
-            int vv[4];
-            double nd[4], dv[4];
-            bool ok[4];
+          if (sub == 0) atomicAnd(&bcur[u >> 5], ~(1u << (u & 31)));   // popped
+          for (int e0 = beg + sub; e0 < end; e0 += UNR * LPV) {
+            int vv[UNR];
+            double nd[UNR], dv[UNR];
+            bool ok[UNR];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < UNR; ++k) {
               const int e = e0 + k * LPV;
               ok[k] = e < end;
               vv[k] = ok[k] ? indices[e] : 0;
               nd[k] = ok[k] ? du + wts[e] : 0.0;
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dv[k] = ok[k] ? __ldcg(dist + vv[k]) : 0.0;
+            for (int k = 0; k < UNR; ++k) dv[k] = ok[k] ? __ldcg(dist + vv[k]) : 0.0;
             // the (rare) updates in three batched levels -- all atomicMin of the four arcs, then all
             // membership atomicOr, then the queue stores -- so that their L2 round trips overlap
             // instead of following one another (they were a third of the kernel's stall samples)
-            bool imp[4];
-            double oldv[4];
+            bool imp[UNR];
+            double oldv[UNR];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) imp[k] = ok[k] && nd[k] < dv[k];
+            for (int k = 0; k < UNR; ++k) imp[k] = ok[k] && nd[k] < dv[k];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) oldv[k] = imp[k] ? atomic_min_pos_f64(dist + vv[k], nd[k]) : 0.0;
-            unsigned int prev[4];
+            for (int k = 0; k < UNR; ++k) oldv[k] = imp[k] ? atomic_min_pos_f64(dist + vv[k], nd[k]) : 0.0;
+            unsigned int prev[UNR];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < UNR; ++k) {
               imp[k] = imp[k] && nd[k] < oldv[k];
               const unsigned int bit = 1u << (vv[k] & 31);
               unsigned int* bm = nd[k] < thr ? bnext : bfar;
               prev[k] = imp[k] ? (atomicOr(&bm[vv[k] >> 5], bit) & bit) : 1u;
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < UNR; ++k) {
               if (!prev[k]) {
                 if (nd[k] < thr) qb[atomicAdd(&s_cnt[p ^ 1], 1)] = vv[k];
                 else far[atomicAdd(&s_cnt_far, 1)] = vv[k];
@@ -775,11 +778,12 @@ extern "C" {
 static int g_sssp_ctas_per_sm = 4;
 // 0: warp per vertex (512 thr), 1: flat thread per arc (512 thr),
 // 2..7: group kernels (threads, lanes per vertex) = (512,8) (256,8) (128,8) (256,32) (128,32) (256,16)
-static int g_sssp_variant = 4;
-static const int kVariantThreads[8] = {512, 512, 512, 256, 128, 256, 128, 256};
+// 8, 9: (128,8) with five / six arcs in flight per lane
+static int g_sssp_variant = 8;
+static const int kVariantThreads[12] = {512, 512, 512, 256, 128, 256, 128, 256, 128, 128, 128, 128};
 
 int pb200_sssp_set_variant(int v) {
-  if (v < 0 || v > 7) { set_error_msg("pb200_sssp_set_variant: 0..7"); return -1; }
+  if (v < 0 || v > 11) { set_error_msg("pb200_sssp_set_variant: 0..11"); return -1; }
   g_sssp_variant = v;
   return 0;
 }
@@ -811,15 +815,19 @@ int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, l
   if (n >= 1073741823LL) { set_error_msg("pb200_sssp_multi: n too large"); return -1; }
   if (!(delta > 0.0)) { set_error_msg("pb200_sssp_multi: delta must be > 0"); return -1; }
   const int grid = pb200_sssp_num_ctas(n_sources);
-#define PB_SSSP_GROUP(T, L)                                                                             \
-  sssp_group_kernel<T, L><<<grid, T, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources, \
-                                                               n_sources, delta, D, q, bits, stats)
+#define PB_SSSP_GROUP(...)                                                                          \
+  sssp_group_kernel<__VA_ARGS__><<<grid, kVariantThreads[g_sssp_variant], 0, (cudaStream_t)stream>>>( \
+      indptr, indices, wts, (int)n, sources, n_sources, delta, D, q, bits, stats)
   if (g_sssp_variant == 2) PB_SSSP_GROUP(512, 8);
   else if (g_sssp_variant == 3) PB_SSSP_GROUP(256, 8);
   else if (g_sssp_variant == 4) PB_SSSP_GROUP(128, 8);
   else if (g_sssp_variant == 5) PB_SSSP_GROUP(256, 32);
   else if (g_sssp_variant == 6) PB_SSSP_GROUP(128, 32);
   else if (g_sssp_variant == 7) PB_SSSP_GROUP(256, 16);
+  else if (g_sssp_variant == 8) PB_SSSP_GROUP(128, 8, 5, 9);    // five arcs per lane: degree <= 40 in one pass, 56 registers
+  else if (g_sssp_variant == 9) PB_SSSP_GROUP(128, 8, 6, 8);
+  else if (g_sssp_variant == 10) PB_SSSP_GROUP(128, 16, 3, 9);
+  else if (g_sssp_variant == 11) PB_SSSP_GROUP(128, 4, 10, 9);
 #undef PB_SSSP_GROUP
   else if (g_sssp_variant == 1)
     sssp_flat_kernel<<<grid, SSSP_THREADS, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources,

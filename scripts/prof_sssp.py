@@ -48,9 +48,9 @@ Dref = run("csr v4 (128 thr)")
 if "--one" in sys.argv:
     sys.exit(0)
 if "--small-delta" in sys.argv:
-    dc.SSSP_MODE = "csr"; lib.pb200_sssp_set_variant(4)
+    dc.SSSP_MODE = "csr"; lib.pb200_sssp_set_variant(8)
     for mult in (1.5, 2.0, 2.5, 3.0, 4.0, 5.0):
-        run("csr v4", mult)
+        run("csr v8", mult)
     sys.exit(0)
 if "--sources" in sys.argv:
     dc.SSSP_MODE = "arcrec"; dc.SSSP_THREADS = None
@@ -66,7 +66,7 @@ if "--delta" in sys.argv:
             run("auto", mult, nsrc=ns)
     sys.exit(0)
 if "--variants" in sys.argv:
-    for v in (2, 3, 5, 6, 7, 4):
+    for v in (10, 11, 8, 4):
         lib.pb200_sssp_set_variant(v)
         D = run(f"csr variant {v}")
         print("   identical:", bool(torch.equal(D, Dref)), flush=True)
