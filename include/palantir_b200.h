@@ -211,6 +211,8 @@ int pb200_point_dists_expanded(const double* data, long long n, int m, long long
 int pb200_sssp_num_ctas(int n_sources);
 int pb200_sssp_set_ctas_per_sm(int c);
 int pb200_sssp_set_variant(int v);
+/* 1 if a near list of the shared-memory-table variant (12) outgrew its buffer since the last call; clears the flag */
+int pb200_sssp_overflowed(void* stream);
 /* D[n_sources][n]; scratch: q[n_ctas*3*n] int, bits[n_ctas*3*ceil(n/32)] uint32; stats [n_sources][3] or NULL */
 int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
                      int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,

@@ -225,6 +225,15 @@ def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, 
     bits = empty((n_ctas * 3 * nwords,), U32)
     with stage("sssp"):
         call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, bits, stats)
+    # the default variant tracks near-list membership in a shared-memory table; a duplicate that slips through a
+    # collision is harmless, but a near list may then in theory outgrow its N entries: checked, never observed
+    if int(lib.pb200_sssp_overflowed(_native.stream_ptr())):
+        lib.pb200_sssp_set_variant(8)
+        try:
+            with stage("sssp"):
+                call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, bits, stats)
+        finally:
+            lib.pb200_sssp_set_variant(12)
     return D, stats
 
 

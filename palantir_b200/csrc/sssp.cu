@@ -232,13 +232,23 @@ __global__ void __launch_bounds__(SSSP_THREADS) sssp_flat_kernel(
 // (two block barriers per round).  Distances are re-read when the vertex is expanded, so later
 // vertices of a round see the improvements made by earlier ones (fewer re-relaxations than a
 // snapshot of the whole frontier).
-template <int THREADS, int LPV, int UNR = 4, int MINB = 0>
+// HASH: membership in the next near list is tracked in a small shared-memory table instead of a global
+// bitmap: slot v mod 1024 holds (round << 32 | v) of the last push that hashed there; a push finding its own
+// tag is a duplicate of this round and is dropped.  A collision only lets a duplicate through (expanded twice
+// next round: harmless), it can never drop a vertex, because tags of different rounds differ.  The test
+// costs a shared-memory atomic instead of an L2 one -- waiting for that result was 19 % of the stall samples.
+// The far pile keeps its exact global bitmap (its entries live for many rounds).
+__device__ int g_sssp_overflow;
+
+template <int THREADS, int LPV, int UNR = 4, int MINB = 0, bool HASH = false>
 __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
     const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ wts, int n,
     const long long* __restrict__ sources, int n_sources, double delta, double* __restrict__ D,
     int* __restrict__ q_all, unsigned int* __restrict__ bits_all, long long* __restrict__ stats) {
   constexpr int NW = THREADS / 32;
   constexpr int NG = THREADS / LPV;
+  constexpr int TAB = 1024;
+  __shared__ unsigned long long s_tab[HASH ? TAB : 1];
   __shared__ int s_cnt[2];
   __shared__ int s_cnt_far;
   __shared__ double s_thr;
@@ -262,7 +272,12 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
     double* dist = D + (size_t)s * (size_t)n;
     const int src = (int)sources[s];
     for (int i = tid; i < n; i += THREADS) dist[i] = INFINITY;
-    for (int i = tid; i < 3 * nwords; i += THREADS) bnear[0][i] = 0u;
+    if (HASH) {
+      for (int i = tid; i < nwords; i += THREADS) bfar[i] = 0u;
+      for (int i = tid; i < TAB; i += THREADS) s_tab[i] = ~0ull;
+    } else {
+      for (int i = tid; i < 3 * nwords; i += THREADS) bnear[0][i] = 0u;
+    }
     __syncthreads();
     int p = 0;
     if (tid == 0) {
@@ -276,8 +291,9 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
 
     for (;;) {
       for (;;) {
-        const int cnt = s_cnt[p];
+        int cnt = s_cnt[p];
         if (cnt == 0) break;
+        if (HASH && cnt > n) cnt = n;        // overflow of the list was flagged when it happened
         ++rounds;
         const double thr = s_thr;
         const int* qa = qbuf[p];
@@ -291,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
           const int u = qa[i];
           const double du = __ldcg(dist + u);
           const int beg = indptr[u], end = indptr[u + 1];
-          if (sub == 0) atomicAnd(&bcur[u >> 5], ~(1u << (u & 31)));   // popped
+          if (!HASH && sub == 0) atomicAnd(&bcur[u >> 5], ~(1u << (u & 31)));   // popped
           for (int e0 = beg + sub; e0 < end; e0 += UNR * LPV) {
             int vv[UNR];
             double nd[UNR], dv[UNR];
@@ -319,14 +335,24 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
             for (int k = 0; k < UNR; ++k) {
               imp[k] = imp[k] && nd[k] < oldv[k];
               const unsigned int bit = 1u << (vv[k] & 31);
-              unsigned int* bm = nd[k] < thr ? bnext : bfar;
-              prev[k] = imp[k] ? (atomicOr(&bm[vv[k] >> 5], bit) & bit) : 1u;
+              if (HASH && nd[k] < thr) {
+                const unsigned long long tag = ((unsigned long long)rounds << 32) | (unsigned int)vv[k];
+                prev[k] = imp[k] ? (atomicExch(&s_tab[vv[k] & (TAB - 1)], tag) == tag ? 1u : 0u) : 1u;
+              } else {
+                unsigned int* bm = nd[k] < thr ? bnext : bfar;
+                prev[k] = imp[k] ? (atomicOr(&bm[vv[k] >> 5], bit) & bit) : 1u;
+              }
             }
 #pragma unroll
             for (int k = 0; k < UNR; ++k) {
               if (!prev[k]) {
-                if (nd[k] < thr) qb[atomicAdd(&s_cnt[p ^ 1], 1)] = vv[k];
-                else far[atomicAdd(&s_cnt_far, 1)] = vv[k];
+                if (nd[k] < thr) {
+                  const int pos = atomicAdd(&s_cnt[p ^ 1], 1);
+                  if (!HASH || pos < n) qb[pos] = vv[k];
+                  else g_sssp_overflow = 1;
+                } else {
+                  far[atomicAdd(&s_cnt_far, 1)] = vv[k];
+                }
               }
             }
           }
@@ -379,7 +405,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
         if (to_near) {
           qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = v;
           atomicAnd(&bfar[v >> 5], ~(1u << (v & 31)));
-          atomicOr(&bcur[v >> 5], 1u << (v & 31));
+          if (!HASH) atomicOr(&bcur[v >> 5], 1u << (v & 31));
         }
         if (tid == THREADS - 1) {
           s_base_keep = bk + offk + __popc(mk);
@@ -779,11 +805,11 @@ static int g_sssp_ctas_per_sm = 4;
 // 0: warp per vertex (512 thr), 1: flat thread per arc (512 thr),
 // 2..7: group kernels (threads, lanes per vertex) = (512,8) (256,8) (128,8) (256,32) (128,32) (256,16)
 // 8, 9: (128,8) with five / six arcs in flight per lane
-static int g_sssp_variant = 8;
-static const int kVariantThreads[12] = {512, 512, 512, 256, 128, 256, 128, 256, 128, 128, 128, 128};
+static int g_sssp_variant = 12;
+static const int kVariantThreads[13] = {512, 512, 512, 256, 128, 256, 128, 256, 128, 128, 128, 128, 128};
 
 int pb200_sssp_set_variant(int v) {
-  if (v < 0 || v > 11) { set_error_msg("pb200_sssp_set_variant: 0..11"); return -1; }
+  if (v < 0 || v > 12) { set_error_msg("pb200_sssp_set_variant: 0..12"); return -1; }
   g_sssp_variant = v;
   return 0;
 }
@@ -828,6 +854,7 @@ int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, l
   else if (g_sssp_variant == 9) PB_SSSP_GROUP(128, 8, 6, 8);
   else if (g_sssp_variant == 10) PB_SSSP_GROUP(128, 16, 3, 9);
   else if (g_sssp_variant == 11) PB_SSSP_GROUP(128, 4, 10, 9);
+  else if (g_sssp_variant == 12) PB_SSSP_GROUP(128, 8, 5, 9, true);   // near-list membership in a shared-memory table
 #undef PB_SSSP_GROUP
   else if (g_sssp_variant == 1)
     sssp_flat_kernel<<<grid, SSSP_THREADS, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources,
@@ -837,6 +864,16 @@ int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, l
                                                                     n_sources, delta, D, q, bits, stats);
   PB_CHECK_LAUNCH("sssp_kernel");
   return 0;
+}
+
+// 1 if a near list of the shared-memory-table variant ever outgrew its buffer since the last call (results
+// must then be recomputed with another variant; n entries per list make this a theoretical case); clears the flag.
+int pb200_sssp_overflowed(void* stream) {
+  int h = 0;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(&h, g_sssp_overflow, sizeof(int)) != cudaSuccess) return -1;
+  if (h) { const int z = 0; cudaMemcpyToSymbol(g_sssp_overflow, &z, sizeof(int)); }
+  return h;
 }
 
 // Arc records {v, indptr[v], w} (16 B each, nnz + 64 entries) for pb200_sssp_multi_arcrec.

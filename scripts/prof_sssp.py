@@ -66,7 +66,7 @@ if "--delta" in sys.argv:
             run("auto", mult, nsrc=ns)
     sys.exit(0)
 if "--variants" in sys.argv:
-    for v in (10, 11, 8, 4):
+    for v in (12, 8, 12, 8):
         lib.pb200_sssp_set_variant(v)
         D = run(f"csr variant {v}")
         print("   identical:", bool(torch.equal(D, Dref)), flush=True)
