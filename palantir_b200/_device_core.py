@@ -210,6 +210,20 @@ def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, 
     lib = _native.load()
     stats = zeros((S, 3), I64) if want_stats else None
     nwords = (n + 31) // 32
+    def exact_rerun():
+        # both default kernels track near-list membership in a shared-memory table; a duplicate that slips
+        # through a collision is harmless, but a near list may then in theory outgrow its N entries: checked after
+        # every call, never observed; the bitmap variant (8) has no such case
+        nc = lib.pb200_sssp_num_ctas(S)
+        q2 = empty((nc * 3 * n,), I32)
+        b2 = empty((nc * 3 * nwords,), U32)
+        lib.pb200_sssp_set_variant(8)
+        try:
+            with stage("sssp"):
+                call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q2, b2, stats)
+        finally:
+            lib.pb200_sssp_set_variant(12)
+
     if SSSP_MODE == "arcrec" and (SSSP_THREADS is not None or S <= 740):
         threads = _sssp_threads(S)
         n_ctas = lib.pb200_sssp_arcrec_ctas(S, threads)
@@ -219,21 +233,18 @@ def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, 
             q = empty((n_ctas * 3 * n * 2,), I32)
             bits = empty((n_ctas * 3 * nwords,), U32)
             call("pb200_sssp_multi_arcrec", g.indptr, arcs, n, sources, S, float(delta), threads, D, q, bits, stats)
+        del q, bits, arcs
+        if int(lib.pb200_sssp_overflowed(_native.stream_ptr())):
+            exact_rerun()
         return D, stats
     n_ctas = lib.pb200_sssp_num_ctas(S)
     q = empty((n_ctas * 3 * n,), I32)
     bits = empty((n_ctas * 3 * nwords,), U32)
     with stage("sssp"):
         call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, bits, stats)
-    # the default variant tracks near-list membership in a shared-memory table; a duplicate that slips through a
-    # collision is harmless, but a near list may then in theory outgrow its N entries: checked, never observed
+    del q, bits
     if int(lib.pb200_sssp_overflowed(_native.stream_ptr())):
-        lib.pb200_sssp_set_variant(8)
-        try:
-            with stage("sssp"):
-                call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, bits, stats)
-        finally:
-            lib.pb200_sssp_set_variant(12)
+        exact_rerun()
     return D, stats
 
 

@@ -478,6 +478,8 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
   __shared__ int s_wtot[NW];
   __shared__ int s_wtot2[NW];
   __shared__ int s_base_keep, s_base_near;
+  constexpr int TAB = 1024;                         // near-list membership: see sssp_group_kernel<..., HASH>
+  __shared__ unsigned long long s_tab[TAB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = tid / LPV, sub = tid % LPV;
   int2* qbuf[2];
@@ -485,16 +487,14 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
   qbuf[1] = qbuf[0] + n;
   int2* far = qbuf[1] + n;
   const int nwords = (n + 31) >> 5;
-  unsigned int* bnear[2];
-  bnear[0] = bits_all + (size_t)blockIdx.x * 3 * (size_t)nwords;
-  bnear[1] = bnear[0] + nwords;
-  unsigned int* bfar = bnear[1] + nwords;
+  unsigned int* bfar = bits_all + (size_t)blockIdx.x * 3 * (size_t)nwords + 2 * (size_t)nwords;   // far-pile membership
 
   for (int s = blockIdx.x; s < n_sources; s += gridDim.x) {
     double* dist = D + (size_t)s * (size_t)n;
     const int src = (int)sources[s];
     for (int i = tid; i < n; i += THREADS) dist[i] = INFINITY;
-    for (int i = tid; i < 3 * nwords; i += THREADS) bnear[0][i] = 0u;
+    for (int i = tid; i < nwords; i += THREADS) bfar[i] = 0u;
+    for (int i = tid; i < TAB; i += THREADS) s_tab[i] = ~0ull;
     __syncthreads();
     int p = 0;
     if (tid == 0) {
@@ -508,18 +508,16 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
 
     for (;;) {
       for (;;) {
-        const int cnt = s_cnt[p];
+        int cnt = s_cnt[p];
         if (cnt == 0) break;
+        if (cnt > n) cnt = n;                       // overflow of the list was flagged when it happened
         ++rounds;
         const double thr = s_thr;
         const int2* qa = qbuf[p];
         int2* qb = qbuf[p ^ 1];
-        unsigned int* bcur = bnear[p];
-        unsigned int* bnext = bnear[p ^ 1];
         for (int i = grp; i < cnt; i += NG) {
           const int2 ub = qa[i];
           const int u = ub.x, beg = ub.y;
-          if (sub == 0) atomicAnd(&bcur[u >> 5], ~(1u << (u & 31)));   // popped
           // level 1: own distance, row end and the first 32 arcs, all independent
           SsspArc ar[4];
 #pragma unroll
@@ -547,15 +545,21 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               imp[k] = imp[k] && nd[k] < oldv[k];
-              const unsigned int bit = 1u << (ar[k].v & 31);
-              unsigned int* bm = nd[k] < thr ? bnext : bfar;
-              prev[k] = imp[k] ? (atomicOr(&bm[ar[k].v >> 5], bit) & bit) : 1u;                             // level 4
+              if (nd[k] < thr) {
+                const unsigned long long tag = ((unsigned long long)rounds << 32) | (unsigned int)ar[k].v;
+                prev[k] = imp[k] ? (atomicExch(&s_tab[ar[k].v & (TAB - 1)], tag) == tag ? 1u : 0u) : 1u;   // level 4
+              } else {
+                const unsigned int bit = 1u << (ar[k].v & 31);
+                prev[k] = imp[k] ? (atomicOr(&bfar[ar[k].v >> 5], bit) & bit) : 1u;
+              }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (!prev[k]) {
                 if (nd[k] < thr) {
-                  qb[atomicAdd(&s_cnt[p ^ 1], 1)] = make_int2(ar[k].v, ar[k].beg);
+                  const int pos = atomicAdd(&s_cnt[p ^ 1], 1);
+                  if (pos < n) qb[pos] = make_int2(ar[k].v, ar[k].beg);
+                  else g_sssp_overflow = 1;
                   const char* row = reinterpret_cast<const char*>(arcs + ar[k].beg);
                   prefetch_l2(row); prefetch_l2(row + 128); prefetch_l2(row + 256);
                   prefetch_l2(row + 384); prefetch_l2(row + 512);
@@ -572,7 +576,7 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
           if (sub == 0) relax += end - beg;
         }
         __syncthreads();
-        if (tid == 0) s_cnt[p] = 0;
+        if (tid == 0) s_cnt[p] = 0;  // this buffer is the push target of the round after next
         p ^= 1;
         __syncthreads();
       }
@@ -596,7 +600,6 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
       __syncthreads();
       const double thr2 = s_thr;
       int2* qa = qbuf[p];
-      unsigned int* bcur = bnear[p];
       for (int c0 = 0; c0 < nfar; c0 += THREADS) {
         const int i = c0 + tid;
         int2 vb = make_int2(-1, 0);
@@ -618,7 +621,6 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
         if (to_near) {
           qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = vb;
           atomicAnd(&bfar[vb.x >> 5], ~(1u << (vb.x & 31)));
-          atomicOr(&bcur[vb.x >> 5], 1u << (vb.x & 31));
           prefetch_l2(arcs + vb.y);
         }
         if (tid == THREADS - 1) {
