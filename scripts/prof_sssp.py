@@ -52,6 +52,14 @@ if "--small-delta" in sys.argv:
     for mult in (1.5, 2.0, 2.5, 3.0, 4.0, 5.0):
         run("csr v8", mult)
     sys.exit(0)
+if "--arcrec128" in sys.argv:
+    dc.SSSP_MODE = "arcrec"; dc.SSSP_THREADS = 128
+    for mult in (2.5, 4.0):
+        D = run("arcrec 128", mult)
+        print("   identical:", bool(torch.equal(D, Dref)))
+    dc.SSSP_MODE = "csr"; dc.SSSP_THREADS = None; lib.pb200_sssp_set_variant(12)
+    run("csr v12", 2.5)
+    sys.exit(0)
 if "--sources" in sys.argv:
     for ns in (599, 300, 150, 1):
         dc.SSSP_MODE = "arcrec"; dc.SSSP_THREADS = None
