@@ -261,10 +261,14 @@ __global__ void __launch_bounds__(KD_ROWS) knn_boxed_kernel(const double* __rest
     for (int c = 0; c < M; ++c) x[c] = data[src * M + c];
   }
   if (tid < M) { s_qlo[tid] = box_lo[qtile * M + tid]; s_qhi[tid] = box_hi[qtile * M + tid]; }
+  // the k best so far, UNSORTED: a new candidate overwrites the current worst entry and the new worst is found
+  // by one scan of the k entries (independent loads) -- keeping the list sorted meant shifting it entry by
+  // entry through a chain of dependent local-memory loads, 90 % of the kernel's time; sorted once at the end
   double bd[KD_KMAX];
   int bi[KD_KMAX];
   for (int s = 0; s < k; ++s) { bd[s] = INFINITY; bi[s] = -1; }
   double worst = INFINITY;
+  int wpos = 0;
   if (tid == 0) s_maxworst = INFINITY;
   __syncthreads();
   unsigned long long scanned = 0;
@@ -324,24 +328,46 @@ __global__ void __launch_bounds__(KD_ROWS) knn_boxed_kernel(const double* __rest
       ++scanned;
       const int lim = (int)((n - t0) < KD_TILE ? (n - t0) : KD_TILE);
       if (active && gr < worst) {
-#pragma unroll 4
-        for (int j = 0; j < lim; ++j) {
-          double r = 0.0;
+        // Two phases per tile.  (A) all 128 distances, the candidates below the current k-th distance only
+        // marked in a bit mask: no divergence.  (B) each lane inserts its marked candidates (distance
+        // recomputed, re-tested against the k-th distance it has by then): the warp runs as many insertion
+        // passes as its busiest lane has candidates, not one pass per candidate of any lane -- with the
+        // insertion inside the scan the shifting of the k-entry lists was 90 % of the kernel.
+        for (int w0 = 0; w0 < lim; w0 += 32) {
+          unsigned int mask = 0;
+#pragma unroll 8
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = w0 + jj;
+            double r = 0.0;
 #pragma unroll
-          for (int c = 0; c < M; ++c) {
-            const double df = __dsub_rn(x[c], tile[j][c]);
-            r = __dadd_rn(r, __dmul_rn(df, df));
-          }
-          if (r < worst) {
-            int pos = k - 1;
-            while (pos > 0 && bd[pos - 1] > r) {
-              bd[pos] = bd[pos - 1];
-              bi[pos] = bi[pos - 1];
-              --pos;
+            for (int c = 0; c < M; ++c) {
+              const double df = __dsub_rn(x[c], tile[j < lim ? j : 0][c]);
+              r = __dadd_rn(r, __dmul_rn(df, df));
             }
-            bd[pos] = r;
-            bi[pos] = (int)(t0 + j);
-            worst = bd[k - 1];
+            mask |= (j < lim && r < worst) ? (1u << jj) : 0u;
+          }
+          while (mask) {
+            const int jj = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int j = w0 + jj;
+            double r = 0.0;
+#pragma unroll
+            for (int c = 0; c < M; ++c) {
+              const double df = __dsub_rn(x[c], tile[j][c]);
+              r = __dadd_rn(r, __dmul_rn(df, df));
+            }
+            if (r < worst) {
+              bd[wpos] = r;
+              bi[wpos] = (int)(t0 + j);
+              double mx = bd[0];
+              int mp = 0;
+              for (int s2 = 1; s2 < k; ++s2) {
+                const double v2 = bd[s2];
+                if (v2 > mx) { mx = v2; mp = s2; }
+              }
+              worst = mx;
+              wpos = mp;
+            }
           }
         }
       }
@@ -359,6 +385,14 @@ __global__ void __launch_bounds__(KD_ROWS) knn_boxed_kernel(const double* __rest
     __syncthreads();
   }
   if (active) {
+    // ascending by (distance, index)
+    for (int e = 1; e < k; ++e) {
+      const double d = bd[e];
+      const int ix = bi[e];
+      int f = e - 1;
+      while (f >= 0 && (bd[f] > d || (bd[f] == d && bi[f] > ix))) { bd[f + 1] = bd[f]; bi[f + 1] = bi[f]; --f; }
+      bd[f + 1] = d; bi[f + 1] = ix;
+    }
     const long long row = (long long)blockIdx.x * KD_ROWS + tid;
     for (int s = 0; s < k; ++s) {
       out_idx[row * k + s] = bi[s];
