@@ -506,6 +506,7 @@ LANCZOS_FP32_SHADOW = os.environ.get("PB200_LANCZOS_SHADOW", "1") != "0"
 # per SpMV at 1M cells); PB200_SPMV_WINDOW=1 additionally switches to the shared-memory-window SpMV kernel, which
 # is correct but slower so far (0.43-0.59 ms: 16 warps per SM do not cover the HBM latency of the CSR stream)
 LANCZOS_WINDOWED = os.environ.get("PB200_LANCZOS_WINDOWED", "1") != "0"
+LANCZOS_INITIAL_BASIS = 320       # vectors allocated up front; the basis is re-allocated (doubling) beyond that
 SPMV_WINDOW_KERNEL = os.environ.get("PB200_SPMV_WINDOW", "0") == "1"
 
 
@@ -552,8 +553,10 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
         long_rows = None
     ld = n
     nblk = n // 2048 + 1
-    V = empty((max_basis + 1, ld), F64)
-    V32 = empty((max_basis + 1, ld), F32) if LANCZOS_FP32_SHADOW else None
+    # the basis grows on demand (the cap is ~2000 vectors = 16 GB at 1 M cells; 200 are used there)
+    cap = min(max_basis, max(LANCZOS_INITIAL_BASIS, batch))
+    V = empty((cap + 1, ld), F64)
+    V32 = empty((cap + 1, ld), F32) if LANCZOS_FP32_SHADOW else None
     alpha = zeros((max_basis + 1,), F64)
     beta = zeros((max_basis + 2,), F64)
     w = empty((n,), F64)
@@ -566,6 +569,16 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
     theta = yvec = None
     while m < max_basis:
         steps = min(batch, max_basis - m)
+        if m + steps > cap:
+            cap = min(max_basis, max(2 * cap, m + steps))
+            V_new = empty((cap + 1, ld), F64)
+            V_new[:m + 1].copy_(V[:m + 1])
+            V = V_new
+            if V32 is not None:
+                V32_new = empty((cap + 1, ld), F32)
+                V32_new[:m + 1].copy_(V32[:m + 1])
+                V32 = V32_new
+            del V_new
         with stage("lanczos_steps"):
             call("pb200_lanczos_steps", indptr, indices, svals, n, nnz, long_rows, n_long, V, ld, V32,
                  int(perm is not None and SPMV_WINDOW_KERNEL), m, steps,

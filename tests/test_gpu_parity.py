@@ -252,6 +252,24 @@ def test_early_cell_fallback_matches_reference(pb):
     assert "palantir_pseudotime" in ad.obs.columns          # the fallback run writes into `ad`, as the reference's does
 
 
+def test_lanczos_basis_growth_gives_the_same_eigenpairs(pb):
+    """The Lanczos basis is allocated for 320 vectors and re-allocated when more are needed."""
+    from palantir_b200 import _device as dv
+
+    z = golden("dm_f64_n800_d24.npz")
+    df = pd.DataFrame(z["x"])
+    a = pb.utils.run_diffusion_maps(df, knn=int(z["knn"]), kernel_backend="sklearn")
+    old = dv.LANCZOS_INITIAL_BASIS
+    dv.LANCZOS_INITIAL_BASIS = 1
+    try:
+        b = pb.utils.run_diffusion_maps(df, knn=int(z["knn"]), kernel_backend="sklearn")
+    finally:
+        dv.LANCZOS_INITIAL_BASIS = old
+    assert pb.utils.LAST_INFO["lanczos"]["steps"] > 20            # grew at least once (first allocation: one batch)
+    assert np.array_equal(a["EigenValues"].values, b["EigenValues"].values)
+    assert np.array_equal(a["EigenVectors"].values, b["EigenVectors"].values)
+
+
 def test_run_diffusion_maps_anndata_keys(pb):
     from palantir_b200.compat import AnnDataLike
 
