@@ -181,8 +181,9 @@ def unreachable_count(g: dv.DeviceCSR, start: int):
 
 
 # "arcrec": arc records + L2 prefetch with 256/512 threads per source when few sources are resident
-# (measured 227 ms vs 415 ms at 150 sources, 1 M cells); with > 740 sources the CSR kernel with 128
-# threads per source is as fast (495 vs 527 ms at 1198 sources) and needs half the scratch.  "csr": always CSR.
+# (measured at 1 M cells: 202 vs 320 ms at 150 sources, 262 vs 331 at 300, 303 vs 342 at 599); with > 740 sources
+# the CSR kernel with 128 threads per source wins (363 vs 462 ms at 1198 sources) and needs half the scratch.
+# "csr": always CSR.
 SSSP_MODE = "arcrec"
 SSSP_THREADS = None        # None: chosen from the number of sources
 
