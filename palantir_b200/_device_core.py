@@ -181,8 +181,8 @@ def unreachable_count(g: dv.DeviceCSR, start: int):
 
 
 # "arcrec": arc records + L2 prefetch with 256/512 threads per source when few sources are resident
-# (measured at 1 M cells: 202 vs 320 ms at 150 sources, 262 vs 331 at 300, 303 vs 342 at 599); with > 740 sources
-# the CSR kernel with 128 threads per source wins (363 vs 462 ms at 1198 sources) and needs half the scratch.
+# (measured at 1 M cells: 197 vs 262 ms at 150 sources, 245 vs 271 at 300); from ~450 sources on the CSR kernel with
+# 128 threads per source wins (281 vs 291 ms at 599 sources, 363 vs 462 at 1198) and needs half the scratch.
 # "csr": always CSR.
 SSSP_MODE = "arcrec"
 SSSP_THREADS = None        # None: chosen from the number of sources
@@ -225,7 +225,7 @@ def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, 
         finally:
             lib.pb200_sssp_set_variant(12)
 
-    if SSSP_MODE == "arcrec" and (SSSP_THREADS is not None or S <= 740):
+    if SSSP_MODE == "arcrec" and (SSSP_THREADS is not None or S <= 444):
         threads = _sssp_threads(S)
         n_ctas = lib.pb200_sssp_arcrec_ctas(S, threads)
         arcs = empty(((g.nnz + 64) * 2,), F64)                     # 16-byte records

@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
   constexpr int NG = THREADS / LPV;
   constexpr int TAB = 1024;
   __shared__ unsigned long long s_tab[HASH ? TAB : 1];
+  __shared__ unsigned int s_ftab[HASH ? TAB : 1];     // far pile: vertex last pushed with this hash (see below)
   __shared__ int s_cnt[2];
   __shared__ int s_cnt_far;
   __shared__ double s_thr;
@@ -273,8 +274,7 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
     const int src = (int)sources[s];
     for (int i = tid; i < n; i += THREADS) dist[i] = INFINITY;
     if (HASH) {
-      for (int i = tid; i < nwords; i += THREADS) bfar[i] = 0u;
-      for (int i = tid; i < TAB; i += THREADS) s_tab[i] = ~0ull;
+      for (int i = tid; i < TAB; i += THREADS) { s_tab[i] = ~0ull; s_ftab[i] = ~0u; }
     } else {
       for (int i = tid; i < 3 * nwords; i += THREADS) bnear[0][i] = 0u;
     }
@@ -338,6 +338,12 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
               if (HASH && nd[k] < thr) {
                 const unsigned long long tag = ((unsigned long long)rounds << 32) | (unsigned int)vv[k];
                 prev[k] = imp[k] ? (atomicExch(&s_tab[vv[k] & (TAB - 1)], tag) == tag ? 1u : 0u) : 1u;
+              } else if (HASH) {
+                // far pile: a vertex enters it once (its distance only falls, the threshold only rises), so the
+                // tag is the vertex itself, cleared when it moves to a near list; an evicted tag lets a second
+                // copy into the pile, which is expanded twice at most
+                prev[k] = imp[k] ? (atomicExch(&s_ftab[vv[k] & (TAB - 1)], (unsigned int)vv[k]) == (unsigned int)vv[k] ? 1u : 0u)
+                                 : 1u;
               } else {
                 unsigned int* bm = nd[k] < thr ? bnext : bfar;
                 prev[k] = imp[k] ? (atomicOr(&bm[vv[k] >> 5], bit) & bit) : 1u;
@@ -351,7 +357,9 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
                   if (!HASH || pos < n) qb[pos] = vv[k];
                   else g_sssp_overflow = 1;
                 } else {
-                  far[atomicAdd(&s_cnt_far, 1)] = vv[k];
+                  const int pos = atomicAdd(&s_cnt_far, 1);
+                  if (!HASH || pos < n) far[pos] = vv[k];
+                  else g_sssp_overflow = 1;
                 }
               }
             }
@@ -364,8 +372,9 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
         __syncthreads();
       }
       // ---------------- advance the threshold ----------------
-      const int nfar = s_cnt_far;
+      int nfar = s_cnt_far;
       if (nfar == 0) break;
+      if (HASH && nfar > n) nfar = n;
       ++advances;
       double mn = INFINITY;
       for (int i = tid; i < nfar; i += THREADS) mn = fmin(mn, __ldcg(dist + far[i]));
@@ -404,8 +413,12 @@ __global__ void __launch_bounds__(THREADS, MINB) sssp_group_kernel(
         if (keep) far[bk + offk + __popc(mk & ((1u << lane) - 1u))] = v;
         if (to_near) {
           qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = v;
-          atomicAnd(&bfar[v >> 5], ~(1u << (v & 31)));
-          if (!HASH) atomicOr(&bcur[v >> 5], 1u << (v & 31));
+          if (HASH) {
+            atomicCAS(&s_ftab[v & (TAB - 1)], (unsigned int)v, ~0u);
+          } else {
+            atomicAnd(&bfar[v >> 5], ~(1u << (v & 31)));
+            atomicOr(&bcur[v >> 5], 1u << (v & 31));
+          }
         }
         if (tid == THREADS - 1) {
           s_base_keep = bk + offk + __popc(mk);
@@ -480,21 +493,19 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
   __shared__ int s_base_keep, s_base_near;
   constexpr int TAB = 1024;                         // near-list membership: see sssp_group_kernel<..., HASH>
   __shared__ unsigned long long s_tab[TAB];
+  __shared__ unsigned int s_ftab[TAB];              // far-pile membership, same scheme
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int grp = tid / LPV, sub = tid % LPV;
   int2* qbuf[2];
   qbuf[0] = q_all + (size_t)blockIdx.x * 3 * (size_t)n;
   qbuf[1] = qbuf[0] + n;
   int2* far = qbuf[1] + n;
-  const int nwords = (n + 31) >> 5;
-  unsigned int* bfar = bits_all + (size_t)blockIdx.x * 3 * (size_t)nwords + 2 * (size_t)nwords;   // far-pile membership
 
   for (int s = blockIdx.x; s < n_sources; s += gridDim.x) {
     double* dist = D + (size_t)s * (size_t)n;
     const int src = (int)sources[s];
     for (int i = tid; i < n; i += THREADS) dist[i] = INFINITY;
-    for (int i = tid; i < nwords; i += THREADS) bfar[i] = 0u;
-    for (int i = tid; i < TAB; i += THREADS) s_tab[i] = ~0ull;
+    for (int i = tid; i < TAB; i += THREADS) { s_tab[i] = ~0ull; s_ftab[i] = ~0u; }
     __syncthreads();
     int p = 0;
     if (tid == 0) {
@@ -549,8 +560,8 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
                 const unsigned long long tag = ((unsigned long long)rounds << 32) | (unsigned int)ar[k].v;
                 prev[k] = imp[k] ? (atomicExch(&s_tab[ar[k].v & (TAB - 1)], tag) == tag ? 1u : 0u) : 1u;   // level 4
               } else {
-                const unsigned int bit = 1u << (ar[k].v & 31);
-                prev[k] = imp[k] ? (atomicOr(&bfar[ar[k].v >> 5], bit) & bit) : 1u;
+                prev[k] = imp[k] ? (atomicExch(&s_ftab[ar[k].v & (TAB - 1)], (unsigned int)ar[k].v) == (unsigned int)ar[k].v ? 1u : 0u)
+                                 : 1u;
               }
             }
 #pragma unroll
@@ -564,7 +575,9 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
                   prefetch_l2(row); prefetch_l2(row + 128); prefetch_l2(row + 256);
                   prefetch_l2(row + 384); prefetch_l2(row + 512);
                 } else {
-                  far[atomicAdd(&s_cnt_far, 1)] = make_int2(ar[k].v, ar[k].beg);
+                  const int pos = atomicAdd(&s_cnt_far, 1);
+                  if (pos < n) far[pos] = make_int2(ar[k].v, ar[k].beg);
+                  else g_sssp_overflow = 1;
                 }
               }
             }
@@ -581,8 +594,9 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
         __syncthreads();
       }
       // ---------------- advance the threshold ----------------
-      const int nfar = s_cnt_far;
+      int nfar = s_cnt_far;
       if (nfar == 0) break;
+      if (nfar > n) nfar = n;
       ++advances;
       double mn = INFINITY;
       for (int i = tid; i < nfar; i += THREADS) mn = fmin(mn, __ldcg(dist + far[i].x));
@@ -620,7 +634,7 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
         if (keep) far[bk + offk + __popc(mk & ((1u << lane) - 1u))] = vb;
         if (to_near) {
           qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = vb;
-          atomicAnd(&bfar[vb.x >> 5], ~(1u << (vb.x & 31)));
+          atomicCAS(&s_ftab[vb.x & (TAB - 1)], (unsigned int)vb.x, ~0u);
           prefetch_l2(arcs + vb.y);
         }
         if (tid == THREADS - 1) {
