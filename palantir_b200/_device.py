@@ -195,7 +195,7 @@ class KnnPrep:
     ld: int
 
 
-def principal_axes(x: torch.Tensor, mean: torch.Tensor, n_axes: int = 3, iters: int = 10) -> torch.Tensor:
+def principal_axes(x: torch.Tensor, mean: torch.Tensor, n_axes: int = 3, iters: int = 5) -> torch.Tensor:
     """Leading principal axes of the centred data ([n_axes, d], orthonormal, norm scaled just below 1)
     by power iteration on X^T X with deflation (two passes over X per step, no host sync).  Only the
     *quality* of the pruning depends on them: any orthonormal set gives valid bounds."""

@@ -48,9 +48,9 @@ Dref = run("csr v4 (128 thr)")
 if "--one" in sys.argv:
     sys.exit(0)
 if "--small-delta" in sys.argv:
-    dc.SSSP_MODE = "csr"; lib.pb200_sssp_set_variant(8)
-    for mult in (1.5, 2.0, 2.5, 3.0, 4.0, 5.0):
-        run("csr v8", mult)
+    dc.SSSP_MODE = "csr"; lib.pb200_sssp_set_variant(12)
+    for mult in (1.5, 2.0, 2.5, 3.0, 4.0, 6.0):
+        run("csr v12", mult)
     sys.exit(0)
 if "--arcrec128" in sys.argv:
     dc.SSSP_MODE = "arcrec"; dc.SSSP_THREADS = 128
