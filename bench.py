@@ -163,6 +163,7 @@ def run_gpu_arm(args):
 
     from palantir_b200 import _device as dv
     from palantir_b200 import _native, core, pipeline, utils
+    from palantir_b200 import config as palantir_config
     from palantir_b200.datasets import synth_branching, synth_names
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,6 +217,8 @@ def run_gpu_arm(args):
     # ---- end to end through the public API (`e2e`) ----
     # the step's input matrix lies in page-locked host memory (bench contract); everything else the API
     # touches on the host is ordinary pandas / scipy / numpy
+    if world > 1:
+        palantir_config.HOST_SPARSE_ON_ALL_RANKS = False      # rank 0 materialises the two sparse matrices
     x_host = torch.from_numpy(x).pin_memory().numpy()
     df = pd.DataFrame(x_host, index=names, copy=False)
     term = {names[v]: k for k, v in info["terminals"].items()}
@@ -242,9 +245,10 @@ def run_gpu_arm(args):
     e2e_sec = float(e2e_s.item())
     kern, tmat = res["kernel"], res["T"]
     h2d = x.nbytes + msd.values.nbytes + n * 8                      # PCA matrix, multiscale matrix, Lanczos start
-    d2h = (kern.data.nbytes + kern.indices.nbytes + kern.indptr.nbytes + tmat.data.nbytes + tmat.indices.nbytes +
-           tmat.indptr.nbytes + res["EigenVectors"].values.nbytes + pr.pseudotime.values.nbytes +
-           pr.entropy.values.nbytes + pr.branch_probs.values.nbytes)
+    sparse_bytes = 0 if kern is None else (kern.data.nbytes + kern.indices.nbytes + kern.indptr.nbytes +
+                                           tmat.data.nbytes + tmat.indices.nbytes + tmat.indptr.nbytes)
+    d2h = (sparse_bytes + res["EigenVectors"].values.nbytes + pr.pseudotime.values.nbytes +
+           pr.entropy.values.nbytes + pr.branch_probs.values.nbytes)      # rank 0's bytes are the ones printed
 
     if rank != 0:
         if world > 1:
@@ -351,7 +355,8 @@ def run_gpu_arm(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 kNN candidates; f64 everything else", "data": "synthetic",
         "config": {"workload": _workload_name(n, d), "l2": "inputs larger than L2 (PCA matrix 400 MB, kernel 0.6 GB, "
-                   "distance matrix 9.6 GB)", "parallelism": f"kNN rows and SSSP sources sharded over {world} GPU(s)"},
+                   "distance matrix 9.6 GB)", "parallelism": f"kNN rows and SSSP sources sharded over {world} GPU(s)"
+                   + ("; e2e: kernel and T materialised on the host by rank 0 only (config.HOST_SPARSE_ON_ALL_RANKS = False)" if world > 1 else "")},
         "e2e": {"value": n / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_sec * 1e3, "steps": n_e2e},
         "gpu_launches": int(launches),

@@ -16,3 +16,9 @@ JOBLIB_BACKEND = None
 # "scanpy" | "sklearn".  Both names run the exact-kNN ("sklearn") semantics here: the
 # reference's scanpy branch is an approximate pynndescent search and is not reproducible.
 KERNEL_BACKEND = "scanpy"
+
+# Multi-GPU runs (one process per GPU): the two sparse results of run_diffusion_maps (kernel and T, 1.3 GB at
+# 1 M cells) are brought to the host on every rank, as a single-process caller expects.  False: only rank 0
+# materialises them ("kernel" / "T" are None elsewhere; everything else is returned on every rank) -- eight
+# processes pulling them through one host at the same time cost more than the whole device step.
+HOST_SPARSE_ON_ALL_RANKS = True

@@ -170,14 +170,18 @@ def run_diffusion_maps(data, n_components: int = 10, knn: int = 30, alpha: float
             raise ValueError("backend must be one of {'scanpy', 'sklearn'}")
         if knn is None or int(knn) <= 0:
             raise ValueError("knn must be a positive integer")
+        from . import _dist
+
         kern = _compute_kernel_device(data_df.values, int(knn), float(alpha))
-        k_home = dv.csr_to_host_async(kern)
-        t_home: list = []
+        want_sparse = palantir_config.HOST_SPARSE_ON_ALL_RANKS or _dist.world()[0] == 0
+        k_home = dv.csr_to_host_async(kern) if want_sparse else None
+        t_home: Optional[list] = [] if want_sparse else None
         tvals, lam, U = _diffusion_maps_device(kern, n_components, seed, t_home)
         vecs = _eigenvector_frame(U)
-        kernel = k_home()
-        _remember_device_copy(kernel, kern)
-        res = {"T": t_home[0](), "EigenVectors": vecs, "EigenValues": pd.Series(lam)}
+        kernel = k_home() if want_sparse else None
+        if kernel is not None:
+            _remember_device_copy(kernel, kern)
+        res = {"T": t_home[0]() if want_sparse else None, "EigenVectors": vecs, "EigenValues": pd.Series(lam)}
     else:
         warn("'data' is a sparse matrix and will be interpreted as kernel. "
              "To avoid this warning compute diffusion maps from a precompued kernel using "

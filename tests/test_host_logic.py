@@ -215,3 +215,35 @@ def test_early_cell_argument_checks_match_the_reference():
         utils.early_cell(ad, "c")
     with pytest.raises(ValueError, match="'fallback_seed' should be an integer"):
         utils.early_cell(ad, "a", fallback_seed=1.5)
+
+
+def test_device_copy_cache_semantics():
+    """palantir_b200/_devcache.py on CPU tensors: hit by identity and by a view of the same memory, miss after an
+    in-place edit, entries die with their host array."""
+    import gc
+
+    import torch
+    from palantir_b200 import _devcache as dc
+
+    dc.clear()
+    a = np.random.default_rng(0).random((5000, 7))
+    t = torch.from_numpy(a.copy())
+    dc.remember(a, t)
+    assert dc.lookup(a) is t
+    df = pd.DataFrame(a, copy=False)
+    assert dc.lookup(df.values) is t                      # DataFrame.values: a new view object over the same memory
+    assert dc.lookup(a.copy()) is None                    # equal numbers, other memory
+    assert dc.lookup(a[:, :3]) is None                    # other shape / strides
+    a[:, 2] *= -1.0                                        # a sign flip of one column must invalidate the copy
+    assert dc.lookup(a) is None
+    a[:, 2] *= -1.0
+    assert dc.lookup(a) is t                               # restored bit for bit: valid again
+    a[17, 3] += 1.0                                        # a single-element edit is caught when it is in the sample ...
+    b = np.zeros((3, 3)); dc.remember(b, torch.zeros(3, 3))
+    b[1, 1] = 5.0
+    assert dc.lookup(b) is None                            # ... and always for small arrays (every element is sampled)
+    n_before = len(dc._ENTRIES)
+    del a, df, b
+    gc.collect()
+    assert len(dc._ENTRIES) < n_before
+    dc.clear()
