@@ -247,3 +247,81 @@ def test_device_copy_cache_semantics():
     gc.collect()
     assert len(dc._ENTRIES) < n_before
     dc.clear()
+
+
+def _warning_texts(fn):
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        out = fn()
+    return out, [str(x.message) for x in w]
+
+
+def test_normalize_cell_identifiers_reference_scenarios():
+    """The scenarios of the reference's tests/test_validation.py:250-437, one by one."""
+    from palantir_b200 import config
+    from palantir_b200.validation import normalize_cell_identifiers as norm
+
+    obs_str = pd.Index(["cell_A", "cell_B", "cell_C", "cell_D", "cell_E"])
+    obs_int = pd.Index([100, 200, 300, 400, 500])
+    (d, nreq, nfound), msgs = _warning_texts(lambda: norm(["cell_A", "cell_C", "cell_E"], obs_str, context="test"))
+    assert (nreq, nfound) == (3, 3) and set(d) == {"cell_A", "cell_C", "cell_E"} and set(d.values()) == {""} and not msgs
+    (d, nreq, nfound), msgs = _warning_texts(lambda: norm({"cell_A": "type1", "cell_B": "type2"}, obs_str, context="test"))
+    assert d == {"cell_A": "type1", "cell_B": "type2"} and (nreq, nfound) == (2, 2) and not msgs
+    (d, nreq, nfound), _ = _warning_texts(lambda: norm(pd.Series(["l1", "l2"], index=["cell_A", "cell_C"]), obs_str))
+    assert d == {"cell_A": "l1", "cell_C": "l2"} and (nreq, nfound) == (2, 2)
+    # integer ids against string names: converted to str, nothing found, the "none found" warning names both types
+    (d, nreq, nfound), msgs = _warning_texts(lambda: norm(pd.Series(["pDC", "ERP"], index=[123, 456]), obs_str, context="test"))
+    assert (nreq, nfound) == (2, 0) and "123" in d and "456" in d
+    assert any("None of the 2 requested cells were found" in m for m in msgs)
+    # string ids against integer names: names compared as strings, with the mismatch warning
+    (d, nreq, nfound), msgs = _warning_texts(lambda: norm(["100", "300", "500"], obs_int, context="test"))
+    assert (nreq, nfound) == (3, 3) and set(d) == {"100", "300", "500"}
+    assert any("Cell identifiers are strings but data.obs_names contains integers" in m for m in msgs)
+    (d, nreq, nfound), msgs = _warning_texts(lambda: norm([100, 300, 500], obs_int, context="test"))
+    assert (nreq, nfound) == (3, 3) and set(d) == {100, 300, 500} and not msgs
+    (d, nreq, nfound), msgs = _warning_texts(lambda: norm(["cell_A", "cell_X", "cell_Y"], obs_str[:3], context="test"))
+    assert (nreq, nfound) == (3, 1) and any("Only 1/3 requested cells were found" in m for m in msgs)
+    (d, nreq, nfound), msgs = _warning_texts(lambda: norm(["cell_X", "cell_Y", "cell_Z"], obs_str[:3], context="test"))
+    assert (nreq, nfound) == (3, 0) and any("None of the 3 requested cells were found" in m for m in msgs)
+    config.WARN_ON_CELL_ID_CONVERSION = False
+    try:
+        (d, nreq, nfound), msgs = _warning_texts(lambda: norm(["cell_X", "cell_Y"], obs_str[:2], context="test"))
+        assert (nreq, nfound) == (2, 0) and not msgs
+    finally:
+        config.WARN_ON_CELL_ID_CONVERSION = True
+    config.AUTO_CONVERT_CELL_IDS_TO_STR = False
+    try:
+        (d, nreq, nfound), msgs = _warning_texts(lambda: norm([100, 200], pd.Index(["100", "200", "300"]), context="test"))
+        assert (nreq, nfound) == (2, 0) and any("Automatic conversion is disabled" in m for m in msgs)
+    finally:
+        config.AUTO_CONVERT_CELL_IDS_TO_STR = True
+    for cells in (pd.Index(["cell_A", "cell_C"]), np.array(["cell_A", "cell_C"])):
+        (d, nreq, nfound), _ = _warning_texts(lambda: norm(cells, obs_str[:3], context="test"))
+        assert (nreq, nfound) == (2, 2) and set(d) == {"cell_A", "cell_C"}
+    with pytest.raises(ValueError, match="No cells provided"):
+        norm([], obs_str)
+    with pytest.raises(ValueError, match="Invalid cells format"):
+        norm(12345, obs_str)
+
+
+def test_normalize_cell_identifiers_differential_vs_reference_source():
+    """Where the reference checkout is present (this container, not the GPU box): same return values and the same
+    warning texts as src/palantir/validation.py on a grid of inputs."""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("reference checkout not present")
+    ref_shim.load_reference()
+    ref_norm = sys.modules[ref_shim._PKG + ".validation"].normalize_cell_identifiers
+    from palantir_b200.validation import normalize_cell_identifiers as norm
+
+    obs_sets = [pd.Index(["a", "b", "c"]), pd.Index([1, 2, 3]), pd.Index(["1", "2", "3"])]
+    cell_sets = [["a", "c"], ["a", "zz"], [1, 3], [1, 9], ["1", "2"], {"a": "x", 2: "y"}, pd.Series({"b": "B"}),
+                 pd.Index(["c"]), np.array([3, 2]), pd.Series(["u", "v"], index=[1, 7])]
+    for obs in obs_sets:
+        for cells in cell_sets:
+            got, gw = _warning_texts(lambda: norm(cells, obs, context="ctx"))
+            want, ww = _warning_texts(lambda: ref_norm(cells, obs, context="ctx"))
+            assert got[0] == want[0] and got[1:] == want[1:], (list(obs), cells)
+            assert gw == ww, (list(obs), cells, gw, ww)
