@@ -325,3 +325,33 @@ def test_normalize_cell_identifiers_differential_vs_reference_source():
             want, ww = _warning_texts(lambda: ref_norm(cells, obs, context="ctx"))
             assert got[0] == want[0] and got[1:] == want[1:], (list(obs), cells)
             assert gw == ww, (list(obs), cells, gw, ww)
+
+
+def test_determine_multiscale_space_gap_rules_vs_reference_source():
+    """Eigen-gap rules of utils.py:890-903 (clear gap, no clear gap -> second largest, floor of 3) on the eigenvalue
+    patterns of the reference's tests/test_utils_determine_multiscale_space.py; compared with the reference source
+    itself where the checkout is present."""
+    from palantir_b200 import utils
+
+    rng = np.random.default_rng(4)
+    clear = np.zeros(10); clear[:4] = [0.95, 0.85, 0.75, 0.30]; clear[4:] = np.linspace(0.25, 0.1, 6)
+    flat = np.linspace(0.9, 0.5, 5)
+    first = np.array([0.99, 0.5, 0.45, 0.4, 0.39])              # largest gap after the first value -> second largest
+    cases = [(clear, 2), (flat, 3), (first, 2)]                  # columns = n_eigs - 1
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+
+    ref_fn = None
+    if ref_shim.available():
+        _, ref_utils = ref_shim.load_reference()
+        ref_fn = ref_utils.determine_multiscale_space
+    for ev, want_cols in cases:
+        vecs = pd.DataFrame(rng.random((40, len(ev))), index=[f"c{i}" for i in range(40)])
+        res = {"EigenValues": pd.Series(ev), "EigenVectors": vecs}
+        out = utils.determine_multiscale_space(res)
+        assert out.shape == (40, want_cols) and list(out.index) == list(vecs.index)
+        for n_eigs in (None, 3, 4):
+            mine = utils.determine_multiscale_space(res, n_eigs=n_eigs)
+            if ref_fn is not None:
+                theirs = ref_fn(res, n_eigs=n_eigs)
+                assert np.array_equal(mine.values, theirs.values) and list(mine.index) == list(theirs.index)
