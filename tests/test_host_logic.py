@@ -355,3 +355,14 @@ def test_determine_multiscale_space_gap_rules_vs_reference_source():
             if ref_fn is not None:
                 theirs = ref_fn(res, n_eigs=n_eigs)
                 assert np.array_equal(mine.values, theirs.values) and list(mine.index) == list(theirs.index)
+
+
+def test_every_abi_entry_point_is_documented():
+    """INTEGRATION.md maps every entry point of include/palantir_b200.h to the reference call site it replaces
+    (or lists it as infrastructure): the header and the document must not drift apart."""
+    header = open(os.path.join(ROOT, "include", "palantir_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(pb200_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) > 60
+    missing = [n for n in names if n not in doc and n.rstrip("12") not in doc]
+    assert not missing, missing
