@@ -18,7 +18,12 @@ Parity status: PINNED.  ``oracle/make_golden.py`` runs the reference's own
 source (``/root/reference/src/palantir``, loaded by ``oracle/ref_shim.py``) on
 seeded inputs, checks that this restatement reproduces it, and commits the
 reference outputs as fixtures under ``tests/golden/``; the CPU tests re-check
-the restatement against those fixtures on every run.
+the restatement against those fixtures on every run (bit for bit), and, where the
+reference checkout is present, against the reference source itself on further
+inputs (``tests/test_oracle_golden.py::test_oracle_vs_reference_source_live``:
+bit for bit up to the pseudotime; the fate projection ``np.dot(W.T, B)`` goes
+through BLAS, whose summation order depends on the operands' memory layout, so
+fates and entropy agree to a few ulp there).
 
 Each function cites the reference ``file:line`` it follows.
 """
