@@ -152,6 +152,43 @@ def case_wrappers(core, utils, ms, info, names):
     print("wrappers:", found, dict(ts), "mid found directly:", mid_found, "fallback:", fb)
 
 
+def case_terminal_states(core):
+    """identify_terminal_states and the terminal_states=None branch of run_palantir (core.py:404-491, 566-649)
+    run by the reference itself.  The reference leaves the ARPACK start of the stationary vector to scipy's
+    default, so every case is run twice and must give the same cells both times (the stationary vector is
+    unique; only its last bits depend on the start)."""
+    out = {}
+    cases = []
+    rng = np.random.default_rng(0)
+    cases.append(("rand5", rng.random((2000, 5)) ** 2, 0, 400))
+    rng = np.random.default_rng(2)
+    cases.append(("rand6", rng.random((1500, 6)) ** 2, 0, 300))
+    x, info = synth_branching(3000, 20, seed=3)
+    o = po.run_diffusion_maps(x, 10, 30)
+    cases.append(("branch", po.multiscale_space(o["EigenVectors"], o["EigenValues"]), info["early"], 500))
+    for tag, ms, early, nwp in cases:
+        names = synth_names(ms.shape[0])
+        df = pd.DataFrame(ms, index=names)
+        runs = [core.identify_terminal_states(df, names[early], knn=30, num_waypoints=nwp) for _ in range(2)]
+        assert list(runs[0][0]) == list(runs[1][0]) and list(runs[0][1]) == list(runs[1][1]), tag
+        ts, exc = runs[0]
+        assert len(ts) > 0, tag
+        ot, oe = po.identify_terminal_states(ms, early, knn=30, num_waypoints=nwp)
+        assert sorted(names[ot]) == sorted(ts) and sorted(names[oe]) == sorted(exc), tag
+        pr = core.run_palantir(df, names[early], terminal_states=None, num_waypoints=nwp, knn=30)
+        op = po.run_palantir(ms, early, terminal=None, num_waypoints=nwp, knn=30)
+        assert list(names[op["terminal"]]) == list(pr.branch_probs.columns), tag
+        assert np.abs(op["pseudotime"] - pr.pseudotime.values).max() == 0, tag
+        assert np.abs(op["fate_probs"] - pr.branch_probs.values).max() < 1e-9, tag    # ARPACK start differs
+        out.update({f"{tag}_ms": ms, f"{tag}_early": early, f"{tag}_nwp": nwp,
+                    f"{tag}_terminal": names.get_indexer(pd.Index(ts)), f"{tag}_excluded": names.get_indexer(exc),
+                    f"{tag}_pseudotime": pr.pseudotime.values, f"{tag}_fate_probs": pr.branch_probs.values,
+                    f"{tag}_fate_columns": names.get_indexer(pr.branch_probs.columns),
+                    f"{tag}_entropy": pr.entropy.values})
+        print("terminal states", tag, list(ts), "excluded", len(exc))
+    np.savez_compressed(os.path.join(OUT, "terminal_states.npz"), **out)
+
+
 def main():
     warnings.simplefilter("ignore")
     os.makedirs(OUT, exist_ok=True)
@@ -164,6 +201,7 @@ def main():
     case_diffusion(core, utils, utils_tight, "dm_f64_n800_d24", 800, 24, np.float64)  # f64 brute
     case_reference_known_answers(core)
     case_tiny(core, utils)
+    case_terminal_states(core)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

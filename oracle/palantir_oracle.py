@@ -346,6 +346,25 @@ def terminal_states_from_chain(t: csr_matrix, wp_data: np.ndarray, pt_wp: np.nda
     return np.unique(bnd[np.argmin(dd, axis=0)])
 
 
+def identify_terminal_states(ms: np.ndarray, early: int, knn: int = 30, num_waypoints: int = 1200,
+                             n_jobs: int = -1, max_iterations: int = 25, seed: int = 20):
+    """core.py:404-491 on positions: scale, boundary / start cell, waypoints (no terminal cells joined),
+    pseudotime, waypoint Markov chain, :func:`terminal_states_from_chain`.  Returns
+    ``(terminal cell positions, excluded boundary cell positions)`` -- the boundary cells of the WAYPOINT
+    matrix that are neither terminal nor the start cell (core.py:488-490)."""
+    data = minmax_scale(np.asarray(ms, dtype=np.float64))
+    bnd = boundary_cells(data)
+    start = pick_start_cell(data, bnd, early)
+    wp = assemble_waypoints(max_min_sampling(data, int(num_waypoints), seed), bnd, None, start)
+    pt, _, _ = compute_pseudotime(data, start, knn, wp, n_jobs, max_iterations)
+    wp_data = data[wp, :]
+    chain = markov_chain(wp_data, knn, pt[wp], n_jobs)
+    term = wp[terminal_states_from_chain(chain, wp_data, pt[wp])]
+    wb = wp[boundary_cells(wp_data)]
+    excluded = np.setdiff1d(np.setdiff1d(wb, term), [start])
+    return term, excluded
+
+
 def absorption_probabilities(t: csr_matrix, abs_states: np.ndarray):
     """core.py:694-765 on positions: absorbing rows, ``(I-Q) B = R`` by SuperLU,
     clamp, entropy, identity rows appended for the absorbing states.

@@ -5,10 +5,16 @@ The reference's API hands NumPy / pandas objects from call to call
 drop-in implementation would download every intermediate and upload it again a moment
 later.  When a result array leaves the package its device original is remembered here,
 keyed by the identity of the host array; the next call that receives the same array
-uses the device copy instead of uploading -- but only while a fingerprint of the host
-memory (address, shape, dtype, a strided sample of the values) still matches, so an
-array edited in place (a sign flip, a rescaling) is uploaded again.  Entries die with
-their host array.
+uses the device copy instead of uploading.
+
+This is OPT-IN (``config.REUSE_DEVICE_RESULTS``, default False): host arrays are the
+caller's to edit, and whether one was edited in place can only be known for certain by
+reading all of it again -- which costs as much as uploading it (48-80 MB at 1 M cells:
+6-10 ms either way).  With the switch on, a hit additionally requires a fingerprint of
+the host memory (address, shape, dtype, a strided sample of the values) to match, which
+catches whole-array edits (a sign flip, a rescaling) but not an edit of a few entries:
+only switch it on when the arrays are passed from call to call untouched.  Entries die
+with their host array.
 """
 from __future__ import annotations
 
@@ -31,13 +37,11 @@ def _fingerprint(a: np.ndarray):
             float(np.sum(flat[-512:], dtype=np.float64)))
 
 
-def _base(a: np.ndarray) -> np.ndarray:
-    return a
-
-
 def remember(host: np.ndarray, dev: torch.Tensor) -> None:
     """``dev`` holds the same numbers as ``host`` (row-major, same shape)."""
-    if not isinstance(host, np.ndarray) or host.size == 0:
+    from . import config
+
+    if not config.REUSE_DEVICE_RESULTS or not isinstance(host, np.ndarray) or host.size == 0:
         return
     fp = _fingerprint(host)
     if fp is None:
@@ -52,7 +56,9 @@ def remember(host: np.ndarray, dev: torch.Tensor) -> None:
 
 def lookup(host) -> Optional[torch.Tensor]:
     """Device copy of ``host`` if one is remembered and the host memory is unchanged."""
-    if not isinstance(host, np.ndarray):
+    from . import config
+
+    if not config.REUSE_DEVICE_RESULTS or not isinstance(host, np.ndarray):
         return None
     hit = _ENTRIES.get(id(host))
     if hit is None:

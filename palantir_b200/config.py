@@ -22,3 +22,8 @@ KERNEL_BACKEND = "scanpy"
 # materialises them ("kernel" / "T" are None elsewhere; everything else is returned on every rank) -- eight
 # processes pulling them through one host at the same time cost more than the whole device step.
 HOST_SPARSE_ON_ALL_RANKS = True
+
+# Reuse the device originals of arrays this package returned (eigenvectors, multiscale matrix, kernel) when the
+# very same host objects come back in the next call, instead of uploading them again.  Off by default: an in-place
+# edit of a few entries of such an array cannot be detected without re-reading all of it (see _devcache.py).
+REUSE_DEVICE_RESULTS = False

@@ -31,6 +31,17 @@ __all__ = ["run_palantir", "identify_terminal_states"]
 LAST_INFO: dict = {}
 
 
+def _positions(index: pd.Index, labels, what: str) -> np.ndarray:
+    """Positions of ``labels`` in ``index``; a label that is not a cell of the data raises KeyError, as the
+    reference's ``data.loc[labels]`` does (core.py:209, 355, 501) -- never a -1 that would index before the
+    first row on the device."""
+    pos = index.get_indexer(pd.Index(labels))
+    if (pos < 0).any():
+        missing = [l for l, p_ in zip(labels, pos) if p_ < 0]
+        raise KeyError(f"{what} not found in the data index: {missing[:10]}" + (" ..." if len(missing) > 10 else ""))
+    return np.asarray(pos, dtype=np.int64)
+
+
 def _get_joblib_backend():
     """Kept for API compatibility (core.py:31-58); the B200 path starts no joblib workers."""
     return config.JOBLIB_BACKEND
@@ -120,8 +131,8 @@ def _compute_pseudotime(data: pd.DataFrame, start_cell, knn: int, waypoints: pd.
     if knn is None or int(knn) <= 0:
         raise ValueError("knn must be a positive integer")
     dev = dv.to_device(np.ascontiguousarray(data.values, dtype=np.float64))
-    start_pos = int(np.where(data.index == start_cell)[0][0])
-    wp_pos = data.index.get_indexer(waypoints)
+    start_pos = int(_positions(data.index, [start_cell], "start cell")[0])
+    wp_pos = _positions(data.index, waypoints, "waypoints")
     pt, D, row0, colsum, sdv, perm = _compute_pseudotime_device(dev, start_pos, int(knn), wp_pos, max_iterations)
     if _dist.world()[1] > 1:
         raise NotImplementedError("_compute_pseudotime returns the dense W and is single-GPU only")
@@ -232,6 +243,10 @@ def run_palantir(data, early_cell, terminal_states=None, knn: int = 30, num_wayp
     ms_dev = _devcache.lookup(ms_vals)             # still on the device from determine_multiscale_space?
     if ms_dev is None or ms_dev.shape != ms_vals.shape or ms_dev.dtype != torch.float64:
         ms_dev = dv.to_device(ms_vals if ms_vals.dtype == np.float64 else ms_vals.astype(np.float64))
+    if _dist.world()[1] > 1:
+        # one process per GPU: every rank shards the SAME kNN rows / shortest-path sources, so all of them must
+        # hold rank 0's matrix bit for bit (a last-bit or sign difference would mix rows of different graphs)
+        ms_dev = _dist.broadcast_(ms_dev.contiguous())
     dev = dc.minmax_scale(ms_dev) if scale_components else ms_dev.clone()
 
     # boundary cells and the start cell (core.py:186-192)
@@ -261,7 +276,7 @@ def run_palantir(data, early_cell, terminal_states=None, knn: int = 30, num_wayp
 
     print("Determining pseudotime...")
     start_pos = int(index.get_loc(start_cell))
-    wp_pos = index.get_indexer(waypoints)
+    wp_pos = _positions(index, waypoints, "waypoints / terminal states")
     pt_dev, D, row0, colsum, sdv, perm = _compute_pseudotime_device(dev, start_pos, knn, wp_pos, max_iterations)
 
     print("Entropy and branch probabilities...")
@@ -345,7 +360,7 @@ def identify_terminal_states(ms_data: pd.DataFrame, early_cell, knn: int = 30, n
     waypoints = waypoints.union(dm_boundaries)
     waypoints = pd.Index(waypoints.difference([start_cell]).unique())
     waypoints = pd.Index([start_cell]).append(waypoints)
-    wp_pos = index.get_indexer(waypoints)
+    wp_pos = _positions(index, waypoints, "waypoints")
     pt_dev = _compute_pseudotime_device(dev, int(index.get_loc(start_cell)), int(knn), wp_pos, max_iterations)[0]
     wp_pos_d = dv.to_device(np.ascontiguousarray(wp_pos, dtype=np.int64))
     wp_dev = dc.gather_rows(dev, wp_pos_d)

@@ -47,7 +47,7 @@ def _remember_device_copy(kernel: csr_matrix, kern: "dv.DeviceCSR") -> None:
 
 
 def _device_copy_of(kernel) -> Optional["dv.DeviceCSR"]:
-    hit = getattr(kernel, "_pb200_device", None)
+    hit = getattr(kernel, "_pb200_device", None) if palantir_config.REUSE_DEVICE_RESULTS else None
     if hit is None:
         return None
     kern, fp = hit
@@ -124,6 +124,13 @@ def _diffusion_maps_device(kern: dv.DeviceCSR, n_components: int, seed, t_home: 
         t_home.append(dv.csr_to_host_async(kern, tvals))
     with dv.stage("eigensolver"):
         lam, U, info = dv.lanczos_topk(kern, svals, dis, start, n_components)
+    from . import _dist
+
+    if _dist.world()[1] > 1:
+        # every rank returns rank 0's eigenpairs bit for bit (the ranks go on to shard one job between them)
+        lam_t = _dist.broadcast_(torch.from_numpy(np.ascontiguousarray(lam, dtype=np.float64)).to(U.device))
+        lam = lam_t.cpu().numpy()
+        U = _dist.broadcast_(U.contiguous())
     LAST_INFO["lanczos"] = info
     return tvals, lam, U
 

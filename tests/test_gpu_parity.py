@@ -191,11 +191,32 @@ def test_kernel_edited_in_place_is_uploaded_again(pb):
     assert abs(got["T"] - want["T"]).max() < 1e-15
 
 
-def test_device_copies_are_equivalent_and_never_stale(pb):
-    """Results handed from call to call keep a device copy (palantir_b200/_devcache.py); using it must give
-    the same numbers as the host arrays, and an array edited in place must not be served from the copy."""
+def test_device_copies_are_off_by_default(pb):
+    """config.REUSE_DEVICE_RESULTS defaults to False: every call uploads the host arrays it is given, so an
+    in-place edit of a single entry between two calls is always honoured."""
     from palantir_b200 import _devcache
 
+    assert pb.config.REUSE_DEVICE_RESULTS is False
+    z = golden("dm_f64_n800_d24.npz")
+    res = pb.utils.run_diffusion_maps(pd.DataFrame(z["x"]), knn=int(z["knn"]), kernel_backend="sklearn")
+    assert _devcache.lookup(res["EigenVectors"].values) is None
+    ms = pb.utils.determine_multiscale_space(res)
+    assert _devcache.lookup(ms.values) is None
+    early = ms.index[int(z["early"])]
+    a = pb.core.run_palantir(ms, early, num_waypoints=100, knn=20)
+    ms2 = ms.copy()
+    ms2.iloc[5, 1] += 0.25 * float(ms.iloc[:, 1].std())          # one entry
+    b = pb.core.run_palantir(ms2, early, num_waypoints=100, knn=20)
+    assert not np.array_equal(a.pseudotime.values, b.pseudotime.values)
+
+
+def test_device_copies_are_equivalent_and_never_stale(pb, monkeypatch):
+    """Opt-in (config.REUSE_DEVICE_RESULTS = True): results handed from call to call keep a device copy
+    (palantir_b200/_devcache.py); using it must give the same numbers as the host arrays, and an array edited
+    in place as a whole must not be served from the copy."""
+    from palantir_b200 import _devcache
+
+    monkeypatch.setattr(pb.config, "REUSE_DEVICE_RESULTS", True)
     z = golden("dm_f64_n800_d24.npz")
     res = pb.utils.run_diffusion_maps(pd.DataFrame(z["x"]), knn=int(z["knn"]), kernel_backend="sklearn")
     assert _devcache.lookup(res["EigenVectors"].values) is not None
@@ -385,6 +406,62 @@ def test_run_palantir_reference_api_behaviour(pb):
     ts = pd.Series({"cell_1": "A", "cell_2": "B"})
     pb.core.run_palantir(ad, "cell_0", terminal_states=ts, save_as_df=False)
     assert list(ad.uns["palantir_fate_probabilities_columns"]) == ["A", "B"]
+
+
+@pytest.mark.parametrize("tag", ["rand5", "rand6", "branch"])
+def test_terminal_states_match_reference_fixture(pb, tag):
+    """core.identify_terminal_states / _terminal_states_from_markov_chain and the terminal_states=None branch
+    of run_palantir (reference core.py:404-491, 566-649) against outputs of the reference's own functions
+    (tests/golden/terminal_states.npz).  The device power iteration replaces ARPACK's randomly started k=1 solve:
+    the stationary vector is unique, so cells must be identical and fates agree to solver accuracy."""
+    from palantir_b200.datasets import synth_names
+
+    z = golden("terminal_states.npz")
+    ms, early, nwp = z[f"{tag}_ms"], int(z[f"{tag}_early"]), int(z[f"{tag}_nwp"])
+    names = synth_names(ms.shape[0])
+    df = pd.DataFrame(ms, index=names)
+    term, exc = pb.core.identify_terminal_states(df, names[early], knn=30, num_waypoints=nwp)
+    assert sorted(names.get_indexer(pd.Index(term))) == sorted(z[f"{tag}_terminal"])
+    assert sorted(names.get_indexer(exc)) == sorted(z[f"{tag}_excluded"])
+    pr = pb.core.run_palantir(df, names[early], terminal_states=None, num_waypoints=nwp, knn=30)
+    assert list(names.get_indexer(pr.branch_probs.columns)) == list(z[f"{tag}_fate_columns"])
+    assert np.max(np.abs(pr.pseudotime.values - z[f"{tag}_pseudotime"])) <= 1e-10
+    assert np.max(np.abs(pr.branch_probs.values - z[f"{tag}_fate_probs"])) <= 1e-8
+    assert np.max(np.abs(pr.entropy.values - z[f"{tag}_entropy"])) <= 1e-8
+
+
+def test_stationary_ranks_vs_oracle_chain(pb, po):
+    """_terminal_states_from_markov_chain (core.py:590-649) on the oracle's own waypoint chain: same positions."""
+    from palantir_b200 import _device as dv
+
+    z = golden("terminal_states.npz")
+    ms, early, nwp = z["rand5_ms"], int(z["rand5_early"]), int(z["rand5_nwp"])
+    data = po.minmax_scale(ms)
+    bnd = po.boundary_cells(data)
+    start = po.pick_start_cell(data, bnd, early)
+    wp = po.assemble_waypoints(po.max_min_sampling(data, nwp, 20), bnd, None, start)
+    pt, _, _ = po.compute_pseudotime(data, start, 30, wp)
+    chain = po.markov_chain(data[wp], 30, pt[wp])
+    want = po.terminal_states_from_chain(chain, data[wp], pt[wp])
+    labels = pd.Index(wp)
+    got = pb.core._terminal_states_from_markov_chain(dv.to_device(np.ascontiguousarray(chain.toarray())),
+                                                     dv.to_device(np.ascontiguousarray(data[wp])), labels, pt[wp])
+    assert sorted(labels.get_indexer(pd.Index(got))) == sorted(want)
+
+
+def test_missing_labels_raise_keyerror(pb, names1500):
+    """A waypoint / terminal label that is not a cell of the data raises KeyError like the reference's
+    data.loc[waypoints] (core.py:209, 355) instead of reaching the device as position -1."""
+    z = golden("palantir_n1500_wp200.npz")
+    names = names1500
+    ms = pd.DataFrame(z["ms"], index=names)
+    early = names[int(z["early"])]
+    with pytest.raises(KeyError):
+        pb.core.run_palantir(ms, early, terminal_states=[names[5], "no_such_cell"], num_waypoints=60)
+    with pytest.raises(KeyError):
+        pb.core.run_palantir(ms, early, num_waypoints=pd.Index([names[3], names[9], "ghost"]))
+    with pytest.raises(KeyError):
+        pb.core._compute_pseudotime(ms, early, knn=10, waypoints=pd.Index([early, "ghost"]), n_jobs=1)
 
 
 # ------------------------------------------------------------------ stage kernels

@@ -217,15 +217,20 @@ def test_early_cell_argument_checks_match_the_reference():
         utils.early_cell(ad, "a", fallback_seed=1.5)
 
 
-def test_device_copy_cache_semantics():
-    """palantir_b200/_devcache.py on CPU tensors: hit by identity and by a view of the same memory, miss after an
-    in-place edit, entries die with their host array."""
+def test_device_copy_cache_semantics(monkeypatch):
+    """palantir_b200/_devcache.py on CPU tensors: off unless config.REUSE_DEVICE_RESULTS; when on, hit by identity
+    and by a view of the same memory, miss after an in-place edit, entries die with their host array."""
     import gc
 
     import torch
     from palantir_b200 import _devcache as dc
+    from palantir_b200 import config
 
     dc.clear()
+    off = np.ones((4, 4))
+    dc.remember(off, torch.ones(4, 4))
+    assert config.REUSE_DEVICE_RESULTS is False and dc.lookup(off) is None and not dc._ENTRIES
+    monkeypatch.setattr(config, "REUSE_DEVICE_RESULTS", True)
     a = np.random.default_rng(0).random((5000, 7))
     t = torch.from_numpy(a.copy())
     dc.remember(a, t)
