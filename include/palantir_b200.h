@@ -228,6 +228,39 @@ int pb200_sssp_multi_arcrec(const int* indptr, const void* arcs, long long n, co
                             int n_sources, double delta, int threads, double* D, void* q, unsigned int* bits,
                             long long* stats, void* stream);
 
+/* ---- the same search decomposed over cells (sssp_cells.cu), for large thin graphs: partition into cells around
+ * seeds, in-cell distance tables from every boundary vertex, per-source search on the overlay graph of the boundary
+ * vertices (pb200_sssp_multi on it), dense min-plus expansion into D.  Replaces core.py:362 like pb200_sssp_multi;
+ * equal to it up to the association of the path sums (~1e-15 relative).  `cells` is a device array of 32-byte
+ * records {int voff, size, nb, ovoff, kept, pad; long long toff} written by the host from the per-cell counts. ---- */
+long long pb200_cells_scratch_bytes(long long n);
+int pb200_cells_partition(const int* indptr, const int* indices, const double* wts, long long n, const int* seeds,
+                          int P, double step, int unit, unsigned long long* key, int* q, int qcap, void* stream);
+int pb200_cells_overflowed(void* stream);
+int pb200_cells_order(const int* indptr, const int* indices, long long n, const unsigned long long* key, int P,
+                      int* cell, int* size, int* nb, long long* arcs, int* perm, int* inv, void* scratch,
+                      long long scratch_bytes, void* stream);
+int pb200_cells_relabel(const int* indptr, const int* indices, const double* wts, long long n, const int* perm,
+                        const int* inv, const int* cell, int* indptr2, int* indices2, double* wts2, int* cell2,
+                        int* nint, void* scratch, long long scratch_bytes, void* stream);
+int pb200_cells_max_cell(void);
+int pb200_cells_local_sssp(const int* indptr2, const int* nint, const int* indices2, const double* wts2,
+                           const void* cells, const int* item_cell, const int* item_src, const long long* item_out,
+                           int n_items, double delta, double* T, void* stream);
+int pb200_cells_overlay_count(const int* indptr2, const int* nint, long long n, const void* cells,
+                              const int* cell2, int n_ov, const int* src_pos, int S, int* pos_ov, int* ov_pos,
+                              int* deg, void* stream);
+int pb200_cells_overlay_scan(const int* deg, int rows_plus_1, int* ov_indptr, void* scratch, long long scratch_bytes,
+                             void* stream);
+int pb200_cells_overlay_fill(const int* indptr2, const int* nint, const int* indices2, const double* wts2,
+                             const void* cells,
+                             const int* cell2, const int* pos_ov, const int* ov_pos, int n_ov, const int* src_pos,
+                             const long long* src_toff, int S, const double* T, const int* ov_indptr,
+                             int* ov_indices, double* ov_wts, void* stream);
+int pb200_cells_expand(const void* cells, const int* cell2, const void* tiles, int n_tiles, const int* dis_pos,
+                       int n_dis, const int* pos_ov, const int* src_pos, const long long* src_toff, const double* T,
+                       const double* Dov, long long ldov, int S, double* D, long long n, void* stream);
+
 /* ---- pseudotime refinement and projection (core.py:368-397, 225-230) ---- */
 int pb200_sum_pow_f64(const double* x, long long count, double shift, int power, double* partial, double* out,
                       void* stream);

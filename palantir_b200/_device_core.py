@@ -198,15 +198,20 @@ def _sssp_threads(n_sources: int) -> int:
     return 128
 
 
-def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, want_stats: bool = False):
-    """D[S, n] shortest-path distances from each source (unreachable = +inf)."""
+def _default_delta(g: dv.DeviceCSR) -> float:
+    # bucket width: measured 2x .. 5x the mean arc weight at 1198 sources / 1 M cells: 393, 390 (2.5x), 397, 403,
+    # 410 ms -- fewer re-relaxations against more threshold advances, a flat optimum
+    delta = 2.5 * float(g.data.mean().item()) if g.nnz else 1.0
+    return delta if delta > 0.0 else 1.0
+
+
+def sssp_per_source(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None,
+                    want_stats: bool = False):
+    """D[S, n] shortest-path distances from each source (unreachable = +inf): one CTA per source walking the
+    whole graph (sssp.cu).  Bit-equal to a heap Dijkstra."""
     n, S = g.n, int(sources.numel())
     if delta is None:
-        # bucket width: measured 2x .. 5x the mean arc weight at 1198 sources / 1 M cells: 393, 390 (2.5x), 397, 403,
-        # 410 ms -- fewer re-relaxations against more threshold advances, a flat optimum
-        delta = 2.5 * float(g.data.mean().item()) if g.nnz else 1.0
-        if not (delta > 0.0):
-            delta = 1.0
+        delta = _default_delta(g)
     D = empty((S, n), F64)
     lib = _native.load()
     stats = zeros((S, 3), I64) if want_stats else None
@@ -247,6 +252,155 @@ def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, 
     if int(lib.pb200_sssp_overflowed(_native.stream_ptr())):
         exact_rerun()
     return D, stats
+
+
+# ---- cell-decomposed search (sssp_cells.cu) ----
+CELLS_MIN_N = 65536           # below this the per-source chain is short enough
+CELL_TARGET = 4096            # vertices per cell aimed at (cells = n / CELL_TARGET seeds)
+CELL_CAP = 16384              # larger cells are dissolved (pb200_cells_max_cell: bitmap of the in-cell kernel)
+CELL_ALPHA = 1.0              # a cell is dissolved when boundary^2 > CELL_ALPHA * its arcs
+CELL_UNIT_GROW = False        # grow the cells breadth-first (every arc counts 1) instead of by arc weight
+CELL_LOCAL_DELTA = 1.0        # bucket width of the in-cell search, in units of the global one
+_CELLINFO = np.dtype([("voff", "<i4"), ("size", "<i4"), ("nb", "<i4"), ("ovoff", "<i4"), ("kept", "<i4"),
+                      ("pad", "<i4"), ("toff", "<i8")])
+LAST_CELLS: dict = {}
+
+
+def sssp_cells(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, want_stats: bool = False,
+               cell_target: Optional[int] = None):
+    """Shortest paths through the cell decomposition of sssp_cells.cu.  Returns (D [S, n] with its COLUMNS IN CELL
+    ORDER, order int32 [n] with order[p] = vertex of g at column p, stats) or None when the graph does not lend
+    itself to it (boundaries too large: not a thin graph) -- the caller then runs sssp_per_source."""
+    n, S = g.n, int(sources.numel())
+    lib = _native.load()
+    if delta is None:
+        delta = _default_delta(g)
+    target = int(cell_target or CELL_TARGET)
+    P = int(max(1, min(2048, round(n / target))))
+    info = {"cells": P}
+    with stage("sssp_partition"):
+        seeds_h = np.unique(((np.arange(P) + 0.5) * n / P).astype(np.int32))
+        P = len(seeds_h)
+        seeds = dv.to_device(seeds_h)
+        key = torch.full((n,), -1, dtype=I64, device=g.indptr.device)
+        qcap = int(max(4096, 8 * (n // P + 1)))
+        q = empty((P * 2 * qcap,), I32)
+        call("pb200_cells_partition", g.indptr, g.indices, g.data, n, seeds, P, float(delta) / 2.5, int(CELL_UNIT_GROW),
+             key, q, qcap)
+        nbytes = int(lib.pb200_cells_scratch_bytes(n))
+        scratch = empty((nbytes,), torch.uint8)
+        cell = empty((n,), I32)
+        counts = zeros((2 * (P + 1),), I32)
+        size_d, nb_d = counts[:P + 1], counts[P + 1:]
+        arcs_d = zeros((P + 1,), I64)
+        order, inv = empty((n,), I32), empty((n,), I32)
+        call("pb200_cells_order", g.indptr, g.indices, n, key, P, cell, size_d, nb_d, arcs_d, order, inv, scratch,
+             nbytes)
+        del q
+        if int(lib.pb200_cells_overflowed(_native.stream_ptr())):
+            return None
+        counts_h = counts.cpu().numpy().astype(np.int64)
+        size_h, nb_h = counts_h[:P + 1], counts_h[P + 1:]
+        arcs_h = arcs_d.cpu().numpy()
+    kept = (np.arange(P + 1) < P) & (size_h > 0) & (size_h <= CELL_CAP) & (nb_h * nb_h <= CELL_ALPHA * arcs_h)
+    ovn = np.where(kept, nb_h, size_h)
+    n_ov = int(ovn.sum())
+    est_arcs = int((nb_h[kept] ** 2).sum() + arcs_h[~kept].sum())
+    info.update(kept=int(kept.sum()), overlay_vertices=n_ov, boundary=int(nb_h[kept].sum()),
+                dissolved_vertices=int(size_h[~kept].sum()), unreached=int(size_h[P]))
+    LAST_CELLS.clear(); LAST_CELLS.update(info)
+    if n_ov > 0.5 * n or est_arcs > 0.5 * g.nnz:
+        return None
+    voff = np.concatenate([[0], np.cumsum(size_h)[:-1]])
+    ovoff = np.concatenate([[0], np.cumsum(ovn)[:-1]])
+    tsz = np.where(kept, nb_h * size_h, 0)
+    toff = np.concatenate([[0], np.cumsum(tsz)[:-1]])
+    t_total = int(tsz.sum())
+    # sources: position in cell order, cell, and whether they need a table row of their own
+    src_pos = inv[sources.long()].contiguous()
+    src_pos_h = src_pos.cpu().numpy().astype(np.int64)
+    src_cell = np.searchsorted(voff, src_pos_h, side="right") - 1
+    src_local = src_pos_h - voff[src_cell]
+    src_interior = kept[src_cell] & (src_local >= nb_h[src_cell])
+    src_rows = np.where(src_interior, size_h[src_cell], 0)
+    src_toff_h = np.where(src_interior, t_total + np.concatenate([[0], np.cumsum(src_rows)[:-1]]), -1).astype(np.int64)
+    t_all = t_total + int(src_rows.sum())
+    ci = np.zeros(P + 1, dtype=_CELLINFO)
+    ci["voff"], ci["size"], ci["nb"], ci["ovoff"], ci["kept"], ci["toff"] = voff, size_h, nb_h, ovoff, kept, toff
+    cells_d = dv.to_device(ci.view(np.uint8))
+    # work items of the in-cell kernel: every (kept cell, boundary vertex) and every interior source
+    kc = np.flatnonzero(kept & (nb_h > 0))
+    it_cell = np.repeat(kc, nb_h[kc])
+    it_src = np.arange(len(it_cell)) - np.repeat(np.cumsum(nb_h[kc]) - nb_h[kc], nb_h[kc])
+    it_out = toff[it_cell] + it_src * size_h[it_cell]
+    sj = np.flatnonzero(src_interior)
+    it_cell = np.concatenate([it_cell, src_cell[sj]])
+    it_src = np.concatenate([it_src, src_local[sj]])
+    it_out = np.concatenate([it_out, src_toff_h[sj]])
+    T = empty((max(1, t_all),), F64)
+    with stage("sssp_tables"):
+        indptr2, indices2, wts2 = empty((n + 1,), I32), empty((g.nnz,), I32), empty((g.nnz,), F64)
+        cell2, nint = empty((n,), I32), empty((n,), I32)
+        call("pb200_cells_relabel", g.indptr, g.indices, g.data, n, order, inv, cell, indptr2, indices2, wts2, cell2,
+             nint, scratch, nbytes)
+        sel = np.argsort(it_cell, kind="stable")          # items of a cell next to each other: its arcs stay in L2 / L1
+        call("pb200_cells_local_sssp", indptr2, nint, indices2, wts2, cells_d, dv.to_device(it_cell[sel].astype(np.int32)),
+             dv.to_device(it_src[sel].astype(np.int32)), dv.to_device(it_out[sel].astype(np.int64)), int(sel.size),
+             float(delta) * CELL_LOCAL_DELTA, T)
+    with stage("sssp_overlay"):
+        src_toff = dv.to_device(src_toff_h)
+        pos_ov, ov_pos = empty((n,), I32), empty((max(1, n_ov),), I32)
+        rows = n_ov + S
+        deg = empty((rows + 1,), I32)
+        ov_indptr = empty((rows + 1,), I32)
+        src_pos32 = src_pos.to(I32).contiguous()
+        call("pb200_cells_overlay_count", indptr2, nint, n, cells_d, cell2, n_ov, src_pos32, S, pos_ov, ov_pos, deg)
+        call("pb200_cells_overlay_scan", deg, rows + 1, ov_indptr, scratch, nbytes)
+        nnz_ov = int(ov_indptr[rows].item())
+        ov_indices, ov_wts = empty((max(1, nnz_ov),), I32), empty((max(1, nnz_ov),), F64)
+        call("pb200_cells_overlay_fill", indptr2, nint, indices2, wts2, cells_d, cell2, pos_ov, ov_pos, n_ov, src_pos32,
+             src_toff, S, T, ov_indptr, ov_indices, ov_wts)
+        ov = dv.DeviceCSR(ov_indptr, ov_indices, ov_wts, rows)
+        ov_sources = torch.arange(n_ov, n_ov + S, dtype=I64, device=g.indptr.device)
+    Dov, stats = sssp_per_source(ov, ov_sources, delta, want_stats)
+    with stage("sssp_expand"):
+        ks = np.flatnonzero(kept)
+        ntile = (size_h[ks] + 255) // 256
+        t_cell = np.repeat(ks, ntile)
+        t_col = (np.arange(len(t_cell)) - np.repeat(np.cumsum(ntile) - ntile, ntile)) * 256
+        tiles = dv.to_device(np.stack([t_cell, t_col], 1).astype(np.int32)) if len(t_cell) else None
+        ds = np.flatnonzero(~kept & (size_h > 0))
+        dis = np.concatenate([np.arange(voff[c], voff[c] + size_h[c]) for c in ds]) if len(ds) else np.zeros(0, np.int64)
+        dis_pos = dv.to_device(dis.astype(np.int32)) if len(dis) else None
+        D = empty((S, n), F64)
+        call("pb200_cells_expand", cells_d, cell2, tiles, int(len(t_cell)), dis_pos, int(len(dis)), pos_ov, src_pos32,
+             src_toff, T, Dov, rows, S, D, n)
+    info.update(overlay_arcs=nnz_ov, table_doubles=t_all, items=int(len(it_cell)))
+    LAST_CELLS.update(info)
+    return D, order, stats
+
+
+def sssp(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = None, want_stats: bool = False,
+         keep_cell_order: bool = False):
+    """D[S, n] shortest-path distances from each source (unreachable = +inf).  Large graphs go through the cell
+    decomposition (sssp_cells), falling back to the per-source kernel when it does not apply.  Returns (D, stats)
+    with the columns in g's vertex order, or -- keep_cell_order=True -- (D, stats, order, inv) with column p holding
+    vertex order[p] and inv[order[p]] = p (both None = g's own order): the caller then saves the pass over D that
+    un-permutes it."""
+    out = None
+    if g.n >= CELLS_MIN_N and SSSP_MODE != "per_source":
+        out = sssp_cells(g, sources, delta, want_stats)
+    if out is None:
+        D, stats = sssp_per_source(g, sources, delta, want_stats)
+        return (D, stats, None, None) if keep_cell_order else (D, stats)
+    D, order, stats = out
+    if keep_cell_order:
+        inv = empty((g.n,), I32)
+        inv[order.long()] = torch.arange(g.n, dtype=I32, device=order.device)
+        return D, stats, order, inv
+    Dt = empty((g.n, D.shape[0]), F64)                  # un-permute the columns: rows of the transpose
+    call("pb200_unpermute_rows_f64", D.t().contiguous(), g.n, D.shape[0], order, Dt)
+    return Dt.t().contiguous(), stats
 
 
 def connect_graph(idx: torch.Tensor, dist: torch.Tensor, data: torch.Tensor, start: int):

@@ -79,8 +79,8 @@ def _compute_pseudotime_device(dev: torch.Tensor, start_pos: int, knn: int, wp_p
     """core.py:353-401 on positions.  When sklearn would pick its kd-tree (<= 15 columns) the
     stage runs on cells ordered along the Morton curve of the leading components (box-pruned exact
     kNN, L2-friendly shortest paths).  Returns (pseudotime [N] in input order, D shard [rows, N] and colsum [N] in
-    WORK order, row0, sdv, perm) with perm = None when work order == input order, else
-    work[i] = input[perm[i]]."""
+    COLUMN order, row0, sdv, perm) with perm = None when column order == input order, else
+    column i = input cell perm[i] (Morton work order composed with the cell order of the shortest-path stage)."""
     print("Shortest path distances using {}-nearest neighbor graph...".format(knn))
     t0 = time.time()
     n, m = dev.shape
@@ -102,7 +102,7 @@ def _compute_pseudotime_device(dev: torch.Tensor, start_pos: int, knn: int, wp_p
     bounds = _dist.shard_bounds(n_wp, size)
     row0, row1 = bounds[rank], bounds[rank + 1]
     sources = dv.to_device(np.ascontiguousarray(wp_w[row0:row1], dtype=np.int64))
-    D, stats = dc.sssp(g, sources, want_stats=dv.PROFILE is not None)
+    D, stats, order, order_inv = dc.sssp(g, sources, want_stats=dv.PROFILE is not None, keep_cell_order=True)
     if dv.PROFILE is not None:
         torch.cuda.synchronize()
         if "scanned" in kstats:
@@ -110,6 +110,7 @@ def _compute_pseudotime_device(dev: torch.Tensor, start_pos: int, knn: int, wp_p
     kstats = {k: v for k, v in kstats.items() if not isinstance(v, torch.Tensor)}
     LAST_INFO["sssp"] = {
         "sources": int(row1 - row0), "arcs": int(g.nnz), "knn": kstats,
+        "cells": dict(dc.LAST_CELLS) if order is not None else None,
         "rounds_mean": float(stats[:, 0].double().mean().item()) if stats is not None and stats.numel() else None,
         "relax_mean": float(stats[:, 1].double().mean().item()) if stats is not None and stats.numel() else None,
         "advances_mean": float(stats[:, 2].double().mean().item()) if stats is not None and stats.numel() else None,
@@ -118,6 +119,10 @@ def _compute_pseudotime_device(dev: torch.Tensor, start_pos: int, knn: int, wp_p
     print("Iteratively refining the pseudotime...")
     start_row = int(np.flatnonzero(wp_w == start_w)[0])
     wp_cells = dv.to_device(np.ascontiguousarray(wp_w, dtype=np.int64))
+    if order is not None:
+        # the cell-decomposed search leaves the columns of D in its own cell order: column p = work vertex order[p]
+        wp_cells = order_inv[wp_cells].long().contiguous()
+        perm = order if perm is None else perm[order.long()].contiguous()
     pt_w, colsum, sdv = dc.refine_pseudotime(D, row0, n_wp, wp_cells, start_row, max_iterations)
     pt = pt_w if perm is None else dc.unpermute_rows(pt_w, perm)
     return pt, D, row0, colsum, sdv, perm

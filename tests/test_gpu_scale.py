@@ -74,10 +74,18 @@ def test_c3_knn_sampled_rows_vs_sklearn_brute(pb, c3):
     got_i = idx[rows_d].cpu().numpy()
     got_d = dist[rows_d].cpu().numpy()
     rd, ri = NearestNeighbors(n_neighbors=31, algorithm="brute").fit(x).kneighbors(x[rows])
-    assert np.array_equal(got_d, rd)
+    # sklearn's chunked DGEMM sums x.y in an order that depends on the chunk shapes, so a 2,000-row query block
+    # may differ from the full-table run (which the kernel reproduces bit for bit, see the fixtures) in the
+    # last bit of d^2 -- visible after the float32 rounding of the distance only for a handful of entries, and
+    # in the self distance (pure cancellation noise around 1e-8)
+    nz = rd[:, 1:] > 0
+    rel = np.abs(got_d[:, 1:] - rd[:, 1:])[nz] / rd[:, 1:][nz]
+    assert rel.max() <= 2.4e-7                                   # two float32 ulps
+    assert np.mean(got_d[:, 1:] != rd[:, 1:]) < 1e-3
+    assert np.max(np.abs(got_d[:, 0] - rd[:, 0])) < 1e-5
     same = (np.sort(got_i, 1) == np.sort(ri, 1)).all(1)
-    ties = np.array([len(np.unique(r)) < 31 for r in rd])
-    assert np.all(same | ties) and ties.sum() < 20
+    near_ties = np.array([np.min(np.diff(r[1:])) <= 2.4e-7 * r[-1] for r in rd])
+    assert np.all(same | near_ties) and (~same).sum() < 20
     c3["knn"] = (idx, dist)
 
 
