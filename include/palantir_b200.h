@@ -185,6 +185,14 @@ int pb200_lanczos_steps(const int* indptr, const int* indices, const double* val
                         int nsteps, double* alpha, double* beta, double* w, double* h, double* partial, double* tmp,
                         void* stream);
 /* U[n][kk] = diag(scale) * sum_j V[j][:] Y[j][kk]  (scale may be NULL), kk <= 32 */
+/* the same steps with partial reorthogonalisation (Gram-Schmidt passes only when the omega recurrence asks for them);
+ * om: 3 * omstride doubles (omstride >= mcap + 2, om[0] = 1, rest 0 before the first step), gate: 2 ints (zero),
+ * counters: 1 int (reorthogonalised steps) */
+int pb200_lanczos_steps_pro(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                            const int* long_rows, int n_long, double* V, long long ldv, float* V32, int windowed,
+                            int j0, int nsteps, double* alpha, double* beta, double* w, double* h, double* partial,
+                            double* tmp, double* om, long long omstride, int* gate, int* counters, double eps,
+                            double thresh, void* stream);
 int pb200_ritz_vectors(const double* V, long long ldv, int m, const double* Y, int kk, const double* scale,
                        double* U, long long n, void* stream);
 /* unit-L2 columns.  scratch: partial[kk * (n/4096+1)], sumsq[kk] */

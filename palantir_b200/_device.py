@@ -506,12 +506,15 @@ LANCZOS_FP32_SHADOW = os.environ.get("PB200_LANCZOS_SHADOW", "1") != "0"
 # per SpMV at 1M cells); PB200_SPMV_WINDOW=1 additionally switches to the shared-memory-window SpMV kernel, which
 # is correct but slower so far (0.43-0.59 ms: 16 warps per SM do not cover the HBM latency of the CSR stream)
 LANCZOS_WINDOWED = os.environ.get("PB200_LANCZOS_WINDOWED", "1") != "0"
+# Gram-Schmidt against the whole basis only when the omega recurrence asks for it (partial reorthogonalisation,
+# pb200_lanczos_steps_pro): ~1 step in 8 instead of every step
+LANCZOS_PRO = os.environ.get("PB200_LANCZOS_PRO", "1") != "0"
 LANCZOS_INITIAL_BASIS = 320       # vectors allocated up front; the basis is re-allocated (doubling) beyond that
 SPMV_WINDOW_KERNEL = os.environ.get("PB200_SPMV_WINDOW", "0") == "1"
 
 
 def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start: torch.Tensor, k: int,
-                 tol: float = 1e-11, batch: int = 20, max_basis: Optional[int] = None):
+                 tol: float = 1e-10, batch: int = 20, max_basis: Optional[int] = None):
     """Largest-magnitude k eigenpairs of S (= those of T) by symmetric Lanczos with
     full re-orthogonalisation.  Returns (eigenvalues desc [k] numpy, U device [n,k] =
     unit-L2 columns of D^-1/2 u, info dict).
@@ -556,7 +559,7 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
     # the basis grows on demand (the cap is ~2000 vectors = 16 GB at 1 M cells; 200 are used there)
     cap = min(max_basis, max(LANCZOS_INITIAL_BASIS, batch))
     V = empty((cap + 1, ld), F64)
-    V32 = empty((cap + 1, ld), F32) if LANCZOS_FP32_SHADOW else None
+    V32 = empty((cap + 1, ld), F32) if (LANCZOS_FP32_SHADOW and not LANCZOS_PRO) else None
     alpha = zeros((max_basis + 1,), F64)
     beta = zeros((max_basis + 2,), F64)
     w = empty((n,), F64)
@@ -564,11 +567,18 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
     partial = empty(((max_basis + 1) * nblk,), F64)
     tmp = empty((1,), F64)
     call("pb200_lanczos_init", start, n, V, V32, partial, tmp)
+    omstride = max_basis + 2
+    om = zeros((3 * omstride,), F64)
+    om[0] = 1.0
+    gate = zeros((2,), I32)
+    counters = zeros((1,), I32)
+    eps_eff = 2.2e-16 * math.sqrt(n)
     m = 0
     info = {"converged": False}
     theta = yvec = None
+    step_batch = batch
     while m < max_basis:
-        steps = min(batch, max_basis - m)
+        steps = min(step_batch, max_basis - m)
         if m + steps > cap:
             cap = min(max_basis, max(2 * cap, m + steps))
             V_new = empty((cap + 1, ld), F64)
@@ -580,9 +590,14 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
                 V32 = V32_new
             del V_new
         with stage("lanczos_steps"):
-            call("pb200_lanczos_steps", indptr, indices, svals, n, nnz, long_rows, n_long, V, ld, V32,
-                 int(perm is not None and SPMV_WINDOW_KERNEL), m, steps,
-                 alpha, beta, w, h, partial, tmp)
+            if LANCZOS_PRO:
+                call("pb200_lanczos_steps_pro", indptr, indices, svals, n, nnz, long_rows, n_long, V, ld, V32,
+                     int(perm is not None and SPMV_WINDOW_KERNEL), m, steps,
+                     alpha, beta, w, h, partial, tmp, om, omstride, gate, counters, eps_eff, 1.5e-8)
+            else:
+                call("pb200_lanczos_steps", indptr, indices, svals, n, nnz, long_rows, n_long, V, ld, V32,
+                     int(perm is not None and SPMV_WINDOW_KERNEL), m, steps,
+                     alpha, beta, w, h, partial, tmp)
         m += steps
         if m < k + 1 and m < max_basis:
             continue
@@ -594,10 +609,15 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
         theta, yvec = theta_all[order], y_all[:, order]
         info.update(steps=m, max_resid=float(resid.max()))
         info.setdefault("history", []).append((m, float(resid.max())))
+        # the residuals fall by orders of magnitude over the last ten steps (1e-4 -> 1e-9 -> 1e-15 at 1 M cells):
+        # once they are small, look every five steps instead of every twenty
+        if resid.max() < 1e-3 * max(1e-3, np.abs(theta).max()):
+            step_batch = max(1, min(batch, 5))
         exhausted = (m >= n) or (b[m - 1] <= 1e-14 * max(1.0, np.abs(theta_all).max()))
         if np.all(resid <= tol * np.maximum(np.abs(theta), 1e-3)) or exhausted:
             info["converged"] = True
             break
+    info["reorthogonalised_steps"] = int(counters.item()) if LANCZOS_PRO else m
     if not info["converged"]:
         raise RuntimeError(
             f"Lanczos did not converge in {m} steps (max residual {info.get('max_resid')}); "

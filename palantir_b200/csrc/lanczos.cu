@@ -265,8 +265,9 @@ constexpr int VCHUNK = 2048;   // elements per block (8 per thread)
 template <typename TV>
 __global__ void __launch_bounds__(VB) multi_dot_kernel(const TV* __restrict__ V, long long ldv, int m,
                                                        const double* __restrict__ w, long long n,
-                                                       double* __restrict__ partial) {
+                                                       double* __restrict__ partial, const int* __restrict__ gate = nullptr) {
   __shared__ double red[VB / 32];
+  if (gate && *gate == 0) return;
   const long long base = (long long)blockIdx.x * VCHUNK;
   double wr[8];
 #pragma unroll
@@ -297,9 +298,11 @@ __global__ void __launch_bounds__(VB) multi_dot_kernel(const TV* __restrict__ V,
 
 // h[c] = sum_b partial[c][b]; optionally hacc[c] += h[c]
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, int nblk, int m,
-                                       double* __restrict__ h, double* __restrict__ hacc) {
+                                       double* __restrict__ h, double* __restrict__ hacc,
+                                       const int* __restrict__ gate = nullptr) {
   const int c = blockIdx.x;
   if (c >= m) return;
+  if (gate && *gate == 0) return;
   __shared__ double red[8];
   double s = 0.0;
   for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += partial[(long long)c * nblk + b];
@@ -318,8 +321,9 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
 template <typename TV>
 __global__ void __launch_bounds__(VB) multi_axpy_kernel(const TV* __restrict__ V, long long ldv, int m,
                                                         const double* __restrict__ h, double* __restrict__ w,
-                                                        long long n) {
+                                                        long long n, const int* __restrict__ gate = nullptr) {
   extern __shared__ double hs[];
+  if (gate && *gate == 0) return;
   for (int c = threadIdx.x; c < m; c += VB) hs[c] = h[c];
   __syncthreads();
   const long long base = (long long)blockIdx.x * VCHUNK;
@@ -363,6 +367,61 @@ __global__ void recurrence_coeffs_kernel(const double* __restrict__ alpha, const
     h2[0] = j > 0 ? beta[j] : 0.0;
     h2[1] = alpha[j];
   }
+}
+
+// Partial reorthogonalisation (Simon 1984, as in PROPACK): om[r][k], r = j mod 3, estimates v_j . v_k.  After the
+// three-term recurrence of step j (alpha[j] known, nrm2 = |w|^2 of the unnormalised v_{j+1}) this computes the
+// estimates for v_{j+1}, and raises gate[0] when one of them exceeds `thresh` (or when the previous step did:
+// the reorthogonalisation is always done on two consecutive vectors, gate[1] carries the second).  A raised gate
+// makes the gated Gram-Schmidt kernels that follow do their work; the estimates are then reset to eps.
+__global__ void lanczos_omega_kernel(const double* __restrict__ alpha, const double* __restrict__ beta, int j,
+                                     const double* __restrict__ nrm2, double* __restrict__ om, long long omstride,
+                                     double eps, double thresh, int* __restrict__ gate, int* __restrict__ counters) {
+  __shared__ double red[8];
+  const double bj1 = sqrt(*nrm2);
+  const double* cur = om + (long long)(j % 3) * omstride;            // omega_{j, .}
+  const double* prv = om + (long long)((j + 2) % 3) * omstride;      // omega_{j-1, .}
+  double* nxt = om + (long long)((j + 1) % 3) * omstride;            // omega_{j+1, .}
+  const double aj = alpha[j], bj = j > 0 ? beta[j] : 0.0;
+  double mx = 0.0;
+  for (int k = threadIdx.x; k < j; k += blockDim.x) {
+    double num = beta[k + 1] * cur[k + 1] + (alpha[k] - aj) * cur[k] - bj * prv[k];
+    if (k > 0) num += beta[k] * cur[k - 1];
+    const double noise = eps * (beta[k + 1] + bj1);
+    num += num >= 0.0 ? noise : -noise;
+    const double o = bj1 > 0.0 ? num / bj1 : 0.0;
+    nxt[k] = o;
+    mx = fmax(mx, fabs(o));
+  }
+  mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+  mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+  mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  __shared__ int s_do;
+  if (threadIdx.x == 0) {
+    double m2 = 0.0;
+    for (int q = 0; q < (int)(blockDim.x >> 5); ++q) m2 = fmax(m2, red[q]);
+    const int forced = gate[1];
+    const int go = (m2 > thresh || forced || !(bj1 > 0.0)) ? 1 : 0;
+    gate[0] = go;
+    gate[1] = (go && !forced) ? 1 : 0;
+    if (go) counters[0] += 1;
+    nxt[j] = j > 0 && bj1 > 0.0 ? eps * beta[1] / bj1 : eps;
+    nxt[j + 1] = 1.0;
+    s_do = go;
+  }
+  __syncthreads();
+  if (s_do)
+    for (int k = threadIdx.x; k <= j; k += blockDim.x) nxt[k] = eps;
+}
+
+// tmp2[0] = |w|^2 recomputed only when the gate is up (w changed); alpha[j] += h[j] likewise
+__global__ void lanczos_fix_alpha_kernel(const double* __restrict__ h, int j, double* __restrict__ alpha,
+                                         const int* __restrict__ gate) {
+  if (threadIdx.x == 0 && *gate) alpha[j] += h[j];
 }
 
 __global__ void vec_mul_kernel(const double* __restrict__ a, const double* __restrict__ b,
@@ -583,6 +642,60 @@ int pb200_lanczos_steps(const int* indptr, const int* indices, const double* val
     PB_CHECK_LAUNCH("multi_axpy_kernel");
     rc = nrm2_into(w, n, partial, tmp, st);
     if (rc) return rc;
+    scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V + (long long)(j + 1) * ldv,
+                                                         V32 ? V32 + (long long)(j + 1) * ldv : nullptr, n, beta + j + 1);
+    PB_CHECK_LAUNCH("scale_by_norm_kernel");
+  }
+  return 0;
+}
+
+// The same recurrence with PARTIAL reorthogonalisation: the Gram-Schmidt pass over the whole basis runs only when
+// the omega recurrence (lanczos_omega_kernel) says that orthogonality is about to drop below `thresh`
+// (~sqrt(machine eps)), on two consecutive steps each time; in between only the three-term recurrence runs.
+// Semi-orthogonality at that level keeps the Ritz values accurate to round-off and the Ritz vectors to ~1e-8
+// (Simon 1984).  om: 3 * (mcap + 2) doubles, om[0] = 1 before the first step; gate: 2 ints, zero before the first step;
+// counters[0] counts the reorthogonalised steps.  Everything else as pb200_lanczos_steps.
+int pb200_lanczos_steps_pro(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                            const int* long_rows, int n_long, double* V, long long ldv, float* V32, int windowed,
+                            int j0, int nsteps, double* alpha, double* beta, double* w, double* h, double* partial,
+                            double* tmp, double* om, long long omstride, int* gate, int* counters, double eps,
+                            double thresh, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = div_up(n, VCHUNK);
+  for (int j = j0; j < j0 + nsteps; ++j) {
+    const int m = j + 1;
+    int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st, windowed, long_rows, n_long);
+    if (rc) return rc;
+    multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V + (long long)j * ldv, ldv, 1, w, n, partial);
+    PB_CHECK_LAUNCH("multi_dot_kernel(alpha)");
+    reduce_partials_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, alpha + j, nullptr);
+    PB_CHECK_LAUNCH("reduce_partials_kernel(alpha)");
+    recurrence_coeffs_kernel<<<1, 32, 0, st>>>(alpha, beta, j, h);
+    PB_CHECK_LAUNCH("recurrence_coeffs_kernel");
+    if (j > 0)
+      multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * 2, st>>>(V + (long long)(j - 1) * ldv, ldv, 2, h, w, n);
+    else
+      multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * 1, st>>>(V, ldv, 1, h + 1, w, n);
+    PB_CHECK_LAUNCH("multi_axpy_kernel(recurrence)");
+    rc = nrm2_into(w, n, partial, tmp, st);
+    if (rc) return rc;
+    lanczos_omega_kernel<<<1, 256, 0, st>>>(alpha, beta, j, tmp, om, omstride, eps, thresh, gate, counters);
+    PB_CHECK_LAUNCH("lanczos_omega_kernel");
+    // gated: one Gram-Schmidt pass against V[0..j], alpha correction, new norm.  The FP64 basis, not its FP32
+    // shadow: here the pass has to bring the overlaps down from ~1e-8 to round-off (the estimates are reset to
+    // eps afterwards), and a shadow vector's 6e-8 rounding error, dotted with a w of norm beta, puts ~1e-9 back
+    multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V, ldv, m, w, n, partial, gate);
+    PB_CHECK_LAUNCH("multi_dot_kernel(gated)");
+    reduce_partials_kernel<<<m, 256, 0, st>>>(partial, nblk, m, h, nullptr, gate);
+    PB_CHECK_LAUNCH("reduce_partials_kernel(gated)");
+    lanczos_fix_alpha_kernel<<<1, 32, 0, st>>>(h, j, alpha, gate);
+    PB_CHECK_LAUNCH("lanczos_fix_alpha_kernel");
+    multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * m, st>>>(V, ldv, m, h, w, n, gate);
+    PB_CHECK_LAUNCH("multi_axpy_kernel(gated)");
+    multi_dot_kernel<double><<<nblk, VB, 0, st>>>(w, 0, 1, w, n, partial, gate);
+    PB_CHECK_LAUNCH("multi_dot_kernel(nrm2, gated)");
+    reduce_partials_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, tmp, nullptr, gate);
+    PB_CHECK_LAUNCH("reduce_partials_kernel(nrm2, gated)");
     scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V + (long long)(j + 1) * ldv,
                                                          V32 ? V32 + (long long)(j + 1) * ldv : nullptr, n, beta + j + 1);
     PB_CHECK_LAUNCH("scale_by_norm_kernel");

@@ -16,9 +16,9 @@ np.random.seed(0)
 v0 = np.random.rand(n)
 start = dv.empty((n,), dv.F64)
 dv.call("pb200_vec_mul", dv.to_device(v0), dsq, start, n)
-for batch in (10,):
+for batch in (20, 20):
     torch.cuda.synchronize(); t0 = time.time()
-    lam, U, inf = dv.lanczos_topk(kern, svals, dis, start, 10, tol=1e-13, batch=batch)
+    lam, U, inf = dv.lanczos_topk(kern, svals, dis, start, 10, batch=batch)
     torch.cuda.synchronize()
     print(f"batch {batch}: {1e3 * (time.time() - t0):.1f} ms, steps {inf['steps']} (windowed {dv.LANCZOS_WINDOWED}, fp32 shadow {dv.LANCZOS_FP32_SHADOW})")
     for m, r in inf["history"]:
