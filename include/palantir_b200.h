@@ -91,6 +91,9 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
                             unsigned long long* tiles_visited, void* stream);
 
 /* rows_out[0..counter) = indices (relative to q0) of flagged rows. */
+/* TF32 tensor peak probe: blocks CTAs x iters bare tcgen05.mma.kind::tf32 128x128x8 instructions (262144 FLOP each);
+ * timed by the caller; the roofline denominator of pb200_knn_candidates_tc (bench.py) */
+int pb200_tf32_peak(int blocks, int iters, void* stream);
 int pb200_knn_flagged_rows(const unsigned char* flag, int nq, int* rows_out, int* counter, void* stream);
 
 /* Exact FP64 brute force for the listed rows.  scratch: n_ctas * n doubles. */

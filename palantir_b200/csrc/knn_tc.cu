@@ -620,6 +620,55 @@ __global__ void knn_prep_tc_kernel(const T* __restrict__ x, long long n, int d, 
   *reinterpret_cast<float4*>(blk + TC_HALF / 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// TF32 tensor peak probe: the same instruction the candidate kernel issues (tcgen05.mma.cta_group::1.kind::tf32,
+// M = N = 128, K = 8, A from tensor memory, B from shared memory), back to back, nothing else: one CTA per SM,
+// `iters` MMAs per CTA rotating over four accumulators, operands resident (no loads inside the loop).  The
+// roofline denominator of the candidate kernel is this kernel's measured FLOP/s (MEASURED_PEAKS.json has no
+// TF32 figure).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* b = reinterpret_cast<float*>(smem_raw);
+  for (int i = tid; i < TC_HALF / 4; i += 128) b[i] = 1.0f + 0.001f * (float)(i & 63);
+  if (tid == 0) { mbar_init(&done_bar, 1); fence_mbar_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  {
+    // A operand: 8 columns of finite values in every lane (columns 504..511)
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16) + 504u;
+    const float4 v = make_float4(1.0f + 0.01f * lane, 0.5f, 0.25f, 0.125f);
+    tc_st4(lane_addr, v);
+    tc_st4(lane_addr + 4, v);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1 && tc_elect_one()) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint64_t bdesc = tc_smem_desc(smem_u32(b));
+    for (int i = 0; i < iters; ++i) tc_mma_tf32_ts(tmem + (uint32_t)(i & 3) * TC_BN, tmem + 504u, bdesc, idesc, i >= 4 ? 1u : 0u);
+    tc_commit(&done_bar);
+  }
+  if (warp == 1) mbar_wait(&done_bar, 0);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
 }  // namespace pb200
 
 using namespace pb200;
@@ -686,6 +735,15 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   PB_CHECK(cudaFuncSetAttribute(knn_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   knn_candidates_tc_kernel<<<div_up(nq, TC_BM), TC_THREADS, smem, st>>>(p);
   PB_CHECK_LAUNCH("knn_candidates_tc_kernel");
+  return 0;
+}
+
+// TF32 tensor peak probe (tf32_peak_kernel): `blocks` CTAs, `iters` 128x128x8 MMAs each = blocks * iters * 262144 FLOP.
+int pb200_tf32_peak(int blocks, int iters, void* stream) {
+  if (blocks < 1 || iters < 4) { set_error_msg("pb200_tf32_peak: need blocks >= 1, iters >= 4"); return -1; }
+  PB_CHECK(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_HALF + 1024));
+  tf32_peak_kernel<<<blocks, 128, TC_HALF + 1024, (cudaStream_t)stream>>>(iters);
+  PB_CHECK_LAUNCH("tf32_peak_kernel");
   return 0;
 }
 
