@@ -561,9 +561,9 @@ def main():
     args = ap.parse_args()
     out = _quiet_stdout()
     if args.config == "c5":
-        from palantir_b200 import bench_magic
+        import bench_c5
 
-        line = bench_magic.run(args)
+        line = bench_c5.run(args)
     else:
         line = run_reference_arm(args) if args.impl == "reference" else run_gpu_arm(args)
     if line is not None:

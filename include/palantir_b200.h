@@ -162,6 +162,12 @@ int pb200_csr_spmv_f64(const int* indptr, const int* indices, const double* vals
                        const double* x, double* y, void* stream);
 int pb200_csr_spmm_f32(const int* indptr, const int* indices, const double* vals, long long n, const float* x,
                        long long ldx, float* y, long long ldy, int g, void* stream);
+/* gene-tiled SpMM for MAGIC at scale (utils.py:791-804): FP32 CSR values (pb200_cast_f64_f32), x / y FP32 or FP64
+ * with 16-byte aligned rows, one launch per tile of 256 / 128 columns; pb200_clip_below = the clip of utils.py:815-821 */
+int pb200_csr_spmm_tiled(const int* indptr, const int* indices, const float* vals32, long long n, const void* x,
+                         long long ldx, void* y, long long ldy, int g, int is_f64, void* stream);
+int pb200_cast_f64_f32(const double* in, float* out, long long n, void* stream);
+int pb200_clip_below(void* a, long long count, double thr, int is_f64, void* stream);
 int pb200_spmv_long_row(void);
 int pb200_csr_spmv_split_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
                              const int* long_rows, int n_long, const double* x, double* y, void* stream);

@@ -255,6 +255,100 @@ __global__ void __launch_bounds__(256) csr_spmm_f32_kernel(const int* __restrict
   }
 }
 
+// Gene-tiled SpMM for MAGIC (utils.py:791-804) at scale: Y[:, g0:g0+GT] = A X[:, g0:g0+GT], one launch per tile of GT
+// gene columns, one warp per row, the row's CSR entries read once per tile (coalesced, FP32 values converted once
+// beforehand), every lane holding 8 columns of the tile (two 16-byte loads per nonzero, 4 nonzeros in flight).
+// With the rows in a locality-preserving order the X rows a neighbourhood of output rows needs (~40 k rows x 1 KB)
+// stay in L2 while the tile is swept, so HBM sees X and Y once per tile: 16.6 GB per product at 1 M cells x 2000
+// genes.  What bounds the kernel is the gather itself: nnz x G x 4 B = 424 GB per product from L2 to the SMs
+// (every (nonzero, gene) pair is a load; the rows of a neighbourhood share almost no neighbours, so shared memory
+// cannot hold anything worth re-using).
+template <typename TX, int VEC>     // VEC elements per 16-byte load: 4 (float) or 2 (double)
+__global__ void __launch_bounds__(256) csr_spmm_tile_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
+                                                            const float* __restrict__ vals, const TX* __restrict__ x,
+                                                            TX* __restrict__ y, long long n, int g, long long ldx,
+                                                            long long ldy, int g0) {
+  constexpr int GT = 64 * VEC;                  // columns per tile: 256 (float) / 128 (double)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= n) return;
+  const int beg = indptr[row], end = indptr[row + 1];
+  const int ca = g0 + lane * VEC, cb = g0 + (lane + 32) * VEC;       // first column of this lane's two vectors
+  const bool fa = ca + VEC <= g, fb = cb + VEC <= g;                 // whole vector inside the matrix
+  TX acc[2 * VEC];
+#pragma unroll
+  for (int k = 0; k < 2 * VEC; ++k) acc[k] = (TX)0;
+  struct alignas(16) V16 { TX v[VEC]; };
+  auto load = [&](const TX* rowp, int c0, bool full, V16& out) {
+    if (full) {
+      out = *reinterpret_cast<const V16*>(rowp + c0);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) out.v[k] = (c0 + k < g) ? rowp[c0 + k] : (TX)0;
+    }
+  };
+  for (int e0 = beg; e0 < end; e0 += 32) {
+    const int e = e0 + lane;
+    const int my_c = e < end ? indices[e] : 0;
+    const float my_v = e < end ? vals[e] : 0.f;
+    const int cnt = end - e0 < 32 ? end - e0 : 32;
+    for (int j0 = 0; j0 < cnt; j0 += 4) {
+      V16 xa[4], xb[4];
+      TX v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u < cnt ? j0 + u : cnt - 1;             // clamped: a repeated entry gets weight 0 below
+        const int c = __shfl_sync(0xffffffffu, my_c, j);
+        const float vv = __shfl_sync(0xffffffffu, my_v, j);
+        v[u] = j0 + u < cnt ? (TX)vv : (TX)0;
+        const TX* rowp = x + (long long)c * ldx;
+        load(rowp, ca, fa, xa[u]);
+        load(rowp, cb, fb, xb[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          acc[k] = fma(v[u], xa[u].v[k], acc[k]);
+          acc[VEC + k] = fma(v[u], xb[u].v[k], acc[VEC + k]);
+        }
+      }
+    }
+  }
+  TX* yr = y + row * ldy;
+  if (fa) {
+    V16 o;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o.v[k] = acc[k];
+    *reinterpret_cast<V16*>(yr + ca) = o;
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) if (ca + k < g) yr[ca + k] = acc[k];
+  }
+  if (fb) {
+    V16 o;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o.v[k] = acc[VEC + k];
+    *reinterpret_cast<V16*>(yr + cb) = o;
+  } else {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) if (cb + k < g) yr[cb + k] = acc[VEC + k];
+  }
+  (void)GT;
+}
+
+__global__ void cast_f64_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+// out[i][:] = (in[i][:] < thr) ? 0 : in[i][:] over an [n][ld] matrix (MAGIC's clip, utils.py:815-821), in place
+template <typename TX>
+__global__ void clip_below_kernel(TX* __restrict__ a, long long count, TX thr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count && a[i] < thr) a[i] = (TX)0;
+}
+
 // ---------------------------------------------------------------------------
 // dense vector kernels
 // ---------------------------------------------------------------------------
@@ -578,6 +672,47 @@ int pb200_csr_spmm_f32(const int* indptr, const int* indices, const double* vals
                        long long ldx, float* y, long long ldy, int g, void* stream) {
   csr_spmm_f32_kernel<<<div_up(n, 8), 256, 0, (cudaStream_t)stream>>>(indptr, indices, vals, x, y, n, g, ldx, ldy);
   PB_CHECK_LAUNCH("csr_spmm_f32_kernel");
+  return 0;
+}
+
+// Gene-tiled SpMM (MAGIC at scale): y[n][ldy] = A x[n][ldx] for the first g columns; vals32: the CSR values in FP32
+// (pb200_cast_f64_f32); x / y FP32 (is_f64 = 0) or FP64; ldx, ldy multiples of 4 (FP32) / 2 (FP64) elements and
+// both bases 16-byte aligned.  One launch per tile of 256 (FP32) / 128 (FP64) columns.
+int pb200_csr_spmm_tiled(const int* indptr, const int* indices, const float* vals32, long long n, const void* x,
+                         long long ldx, void* y, long long ldy, int g, int is_f64, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0 || g <= 0) return 0;
+  const int vec = is_f64 ? 2 : 4;
+  if (ldx % vec != 0 || ldy % vec != 0 || ((uintptr_t)x & 15) || ((uintptr_t)y & 15)) {
+    set_error_msg("pb200_csr_spmm_tiled: leading dimensions / bases must be 16-byte aligned");
+    return -1;
+  }
+  const int gt = 64 * vec;
+  for (int g0 = 0; g0 < g; g0 += gt) {
+    if (is_f64)
+      csr_spmm_tile_kernel<double, 2><<<div_up(n, 8), 256, 0, st>>>(indptr, indices, vals32, (const double*)x, (double*)y,
+                                                                   n, g, ldx, ldy, g0);
+    else
+      csr_spmm_tile_kernel<float, 4><<<div_up(n, 8), 256, 0, st>>>(indptr, indices, vals32, (const float*)x, (float*)y, n,
+                                                                  g, ldx, ldy, g0);
+    PB_CHECK_LAUNCH("csr_spmm_tile_kernel");
+  }
+  return 0;
+}
+
+int pb200_cast_f64_f32(const double* in, float* out, long long n, void* stream) {
+  if (n <= 0) return 0;
+  cast_f64_f32_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  PB_CHECK_LAUNCH("cast_f64_f32_kernel");
+  return 0;
+}
+
+// a[i] = 0 where a[i] < thr (count elements, FP32 or FP64)
+int pb200_clip_below(void* a, long long count, double thr, int is_f64, void* stream) {
+  if (count <= 0) return 0;
+  if (is_f64) clip_below_kernel<double><<<div_up(count, 256), 256, 0, (cudaStream_t)stream>>>((double*)a, count, thr);
+  else        clip_below_kernel<float><<<div_up(count, 256), 256, 0, (cudaStream_t)stream>>>((float*)a, count, (float)thr);
+  PB_CHECK_LAUNCH("clip_below_kernel");
   return 0;
 }
 

@@ -249,13 +249,64 @@ def determine_multiscale_space(dm_res, n_eigs: Union[int, None] = None, eigval_k
     return out
 
 
+MAGIC_CHUNK_GENES = 4096        # gene columns resident on the device at a time (2 x N x chunk x 4 B)
+MAGIC_ORDER_MIN_CELLS = 65536   # from this size on the operator is relabelled into a locality-preserving order
+
+
+def _magic_operator(T, eigenvectors=None):
+    """Device copy of the diffusion operator for MAGIC: CSR with FP32 values (the reference casts T^n to float32,
+    utils.py:791) and -- at scale, when diffusion components are at hand -- relabelled along the Morton curve of the
+    leading components, so that the X rows a neighbourhood of output rows gathers stay in L2.
+    Returns (indptr, indices, vals32, n, perm or None)."""
+    from . import _device_core as dc
+
+    op = dv.csr_from_host(T)
+    n = op.n
+    perm = None
+    indptr, indices, vals = op.indptr, op.indices, op.data
+    if eigenvectors is not None and n >= MAGIC_ORDER_MIN_CELLS and eigenvectors.shape[1] >= 2:
+        comps = np.ascontiguousarray(np.asarray(eigenvectors)[:, 1:4], dtype=np.float64)
+        perm, inv, _ = dc.morton_order(dv.to_device(comps))
+        lens = (op.indptr[1:] - op.indptr[:-1])[perm.long()]
+        indptr = torch.zeros((n + 1,), dtype=dv.I32, device=perm.device)
+        indptr[1:] = torch.cumsum(lens, 0)
+        indices = dv.empty((op.nnz,), dv.I32)
+        vals = dv.empty((op.nnz,), dv.F64)
+        dv.call("pb200_csr_permute", op.indptr, op.indices, op.data, n, perm, inv, indptr, indices, vals)
+    vals32 = dv.empty((op.nnz,), dv.F32)
+    dv.call("pb200_cast_f64_f32", vals, vals32, op.nnz)
+    return indptr, indices, vals32, n, perm
+
+
+def magic_device(operator, x: torch.Tensor, g: int, n_steps: int, clip_threshold: Optional[float] = None) -> torch.Tensor:
+    """T^n_steps X as n_steps successive gene-tiled SpMMs on a device matrix x [n, ld] (FP32 or FP64, ld a multiple
+    of 4, first g columns used; rows in the operator's order).  Returns the result buffer (same shape)."""
+    indptr, indices, vals32, n, _ = operator
+    ld = x.shape[1]
+    cur, nxt = x, torch.empty_like(x)
+    if ld > g:
+        nxt[:, g:] = 0
+    is64 = int(x.dtype == torch.float64)
+    with dv.stage("magic_spmm"):
+        for _ in range(int(n_steps)):
+            dv.call("pb200_csr_spmm_tiled", indptr, indices, vals32, n, cur, ld, nxt, ld, g, is64)
+            cur, nxt = nxt, cur
+        if clip_threshold is not None:
+            dv.call("pb200_clip_below", cur, cur.numel(), float(clip_threshold), is64)
+    return cur
+
+
 def run_magic_imputation(data, dm_res: Union[dict, None] = None, n_steps: int = 3, sim_key: str = "DM_Similarity",
                          expression_key: str = None, imputation_key: str = "MAGIC_imputed_data",
                          n_jobs: int = -1, sparse: bool = True, clip_threshold: float = 1e-2):
-    """MAGIC imputation T^n_steps X (reference utils.py:727-846) as n_steps successive
-    SpMMs with the device-resident operator -- T^n is never materialised (the reference
-    builds it: 1978 nnz/row at n=3).  Return type follows the input type as in the
-    reference; values below clip_threshold are zeroed."""
+    """MAGIC imputation T^n_steps X (reference utils.py:727-846) as n_steps successive SpMMs with the
+    device-resident operator -- T^n is never materialised (the reference builds it: 1978 nnz/row at n=3).
+    The genes are processed in column chunks (a sparse X is densified one chunk at a time, as the reference's
+    100-column chunks do); X keeps its precision (float32 stays float32, float64 stays float64: the reference
+    casts only T^n to float32); with several ranks every rank imputes its own share of the columns.  Return type
+    follows the input type as in the reference; values below clip_threshold are zeroed."""
+    from . import _dist
+
     if is_anndata(data):
         if expression_key is not None:
             if expression_key not in data.layers.keys():
@@ -270,31 +321,65 @@ def run_magic_imputation(data, dm_res: Union[dict, None] = None, n_steps: int = 
     else:
         X = data
         T = None
+    vecs = None
     if dm_res is not None:
         T = dm_res["T"]
+        ev = dm_res.get("EigenVectors") if isinstance(dm_res, dict) else None
+        if ev is not None:
+            vecs = ev.values if isinstance(ev, pd.DataFrame) else np.asarray(ev)
     elif not is_anndata(data):
         raise ValueError("Diffusion map results (dm_res) must be provided if data is not AnnData")
+    elif "DM_EigenVectors" in getattr(data, "obsm", {}):
+        vecs = np.asarray(data.obsm["DM_EigenVectors"])
 
     x_sparse = issparse(X)
-    dense = np.asarray(X.todense()) if x_sparse else np.asarray(X)
-    op = dv.csr_from_host(T)
-    n, g = dense.shape
-    cur = dv.to_device(dense.astype(np.float32))
-    nxt = dv.empty((n, g), dv.F32)
-    with dv.stage("magic_spmm"):
-        for _ in range(int(n_steps)):
-            dv.call("pb200_csr_spmm_f32", op.indptr, op.indices, op.data, n, cur, g, nxt, g, g)
-            cur, nxt = nxt, cur
-    imputed = cur.cpu().numpy()
-    if not x_sparse and dense.dtype == np.float64:
-        imputed = imputed.astype(np.float64)
+    if x_sparse:
+        X = X.tocsc()
+    n, g = X.shape
+    out_dtype = np.float64 if X.dtype == np.float64 else np.float32
+    if vecs is not None and vecs.shape[0] != n:
+        vecs = None
+    operator = _magic_operator(T, vecs)
+    perm = operator[4]
+    perm_l = perm.long() if perm is not None else None
+    rank, world = _dist.world()
+    col_bounds = _dist.shard_bounds(g, world)
+    c_lo, c_hi = col_bounds[rank], col_bounds[rank + 1]
+    pieces = []
+    for c0 in range(c_lo, c_hi, MAGIC_CHUNK_GENES):
+        c1 = min(c_hi, c0 + MAGIC_CHUNK_GENES)
+        w = c1 - c0
+        ld = dv.round_up(w, 4)
+        chunk = X[:, c0:c1].toarray() if x_sparse else np.asarray(X[:, c0:c1])
+        xh = torch.from_numpy(np.ascontiguousarray(chunk, dtype=out_dtype))
+        xd = dv.zeros((n, ld), dv.F64 if out_dtype == np.float64 else dv.F32) if ld != w else \
+            dv.empty((n, ld), dv.F64 if out_dtype == np.float64 else dv.F32)
+        xd[:, :w].copy_(xh, non_blocking=False)
+        if perm_l is not None:
+            xd = xd[perm_l].contiguous()
+        yd = magic_device(operator, xd, w, n_steps, clip_threshold)
+        if perm_l is not None:
+            back = torch.empty_like(yd)
+            back[perm_l] = yd
+            yd = back
+        pieces.append(yd[:, :w])
+        del xd
+    mine = torch.cat(pieces, dim=1) if len(pieces) != 1 else pieces[0]
+    if world > 1:
+        wmax = max(col_bounds[r + 1] - col_bounds[r] for r in range(world))
+        pad = dv.zeros((n, wmax), mine.dtype)
+        pad[:, :mine.shape[1]] = mine
+        full = dv.empty((world, n, wmax), mine.dtype)
+        torch.distributed.all_gather_into_tensor(full, pad)
+        mine = torch.cat([full[r, :, :col_bounds[r + 1] - col_bounds[r]] for r in range(world)], dim=1)
+        if not (palantir_config.HOST_SPARSE_ON_ALL_RANKS or rank == 0):
+            return None
+    imputed = dv.to_host(mine.contiguous())
 
     if sparse:
-        imputed = csr_matrix(np.where(imputed < clip_threshold, 0, imputed))
-    else:
-        imputed[imputed < clip_threshold] = 0
-        if x_sparse:
-            imputed = np.asmatrix(imputed)
+        imputed = csr_matrix(imputed)                   # values below the threshold are already exact zeros
+    elif x_sparse:
+        imputed = np.asmatrix(imputed)
     if is_anndata(data):
         data.layers[imputation_key] = imputed if issparse(imputed) else np.asarray(imputed)
     if isinstance(data, pd.DataFrame):

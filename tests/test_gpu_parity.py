@@ -650,11 +650,47 @@ def test_magic_imputation_vs_oracle(pb, po):
     x = rng.random((600, 37)).astype(np.float32)
     got = pb.utils.run_magic_imputation(x, dm_res=res, n_steps=3, sparse=False)
     ref = po.magic_impute(res["T"], x, 3)
+    assert got.dtype == np.float32
     near_clip = np.abs(ref - 1e-2) < 1e-5
     assert np.max(np.abs(got - ref)[~near_clip]) <= 1e-5
     sp = pb.utils.run_magic_imputation(pd.DataFrame(x), dm_res=res)
     assert isinstance(sp, pd.DataFrame) and sp.shape == x.shape
     assert isinstance(pb.utils.run_magic_imputation(x, dm_res=res), csr_matrix)
+    # float64 X keeps its precision (the reference casts only T^n to float32, utils.py:791)
+    x64 = rng.random((600, 301))                            # more than one 128-column tile, ragged tail
+    got64 = pb.utils.run_magic_imputation(x64, dm_res=res, n_steps=2, sparse=False)
+    ref64 = po.magic_impute(res["T"], x64, 2)
+    assert got64.dtype == np.float64 and ref64.dtype == np.float64
+    near_clip = np.abs(ref64 - 1e-2) < 1e-5
+    assert np.max(np.abs(got64 - ref64)[~near_clip]) <= 1e-5
+    # sparse X: densified chunk by chunk, same numbers, reference's return types
+    xs = csr_matrix(x * (x > 0.7))
+    a = pb.utils.run_magic_imputation(xs, dm_res=res, n_steps=3, sparse=False)
+    b = po.magic_impute(res["T"], np.asarray(xs.todense()), 3)
+    assert isinstance(a, np.matrix) and np.max(np.abs(np.asarray(a) - b)[np.abs(b - 1e-2) > 1e-5]) <= 1e-5
+    assert isinstance(pb.utils.run_magic_imputation(xs, dm_res=res), csr_matrix)
+
+
+def test_magic_imputation_at_scale_with_chunks(pb, monkeypatch):
+    """100 k cells x 700 genes: the operator is relabelled along the diffusion components (locality for the gathers) and
+    the genes go through the device in chunks; T (T (T X)) in FP64 on the host is the yardstick (the reference's
+    T**3 would hold 2e8 entries here)."""
+    from palantir_b200.datasets import synth_branching
+
+    n, g = 100_000, 700
+    x, _ = synth_branching(n, 50, seed=0)
+    res = pb.utils.run_diffusion_maps(pd.DataFrame(x), kernel_backend="sklearn")
+    genes = np.random.default_rng(3).random((n, g), dtype=np.float32)
+    monkeypatch.setattr(pb.utils, "MAGIC_CHUNK_GENES", 300)
+    got = pb.utils.run_magic_imputation(genes, dm_res=res, n_steps=3, sparse=False)
+    t = res["T"]
+    cols = np.r_[0:5, 298:303, 695:700]
+    ref = t @ (t @ (t @ genes[:, cols].astype(np.float64)))
+    assert got.shape == (n, g) and got.dtype == np.float32
+    assert np.max(np.abs(got[:, cols] - ref)) <= 1e-5
+    # without eigenvectors (operator in input order) the numbers are the same
+    got2 = pb.utils.run_magic_imputation(genes[:, :64], dm_res={"T": t}, n_steps=3, sparse=False)
+    assert np.max(np.abs(got2 - got[:, :64])) <= 2e-6
 
 
 # ------------------------------------------------------------------ benchmark-size properties
