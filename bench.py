@@ -350,8 +350,20 @@ def run_gpu_arm(args):
                                                    tmat.data.nbytes + tmat.indices.nbytes + tmat.indptr.nbytes)
             d2h = (sparse_bytes + res["EigenVectors"].values.nbytes + pr.pseudotime.values.nbytes +
                    pr.entropy.values.nbytes + pr.branch_probs.values.nbytes)
+        # size-independent properties of the last device-resident result (not timed)
+        from scipy.stats import spearmanr
+
+        pt = out["pseudotime"].cpu().numpy()
+        fp = out["fate_probs"].cpu().numpy()
+        stride = max(1, n_cells // 200_000)
+        sanity = {"pseudotime_range": [float(pt.min()), float(pt.max())],
+                  "spearman_vs_latent_time": float(spearmanr(pt[::stride], info["time"][::stride])[0]),
+                  "fate_rows_sum_max_dev": float(np.abs(fp.sum(1) - 1.0).max()) if fp.shape[1] else None,
+                  "own_fate_of_terminal_cells": [float(fp[p].max()) for p in term_pos] if fp.shape[1] else None,
+                  "knn_rows_needing_exact_fallback": int((out.get("knn") or {}).get("flagged", 0)),
+                  "eigenvalues": [float(v) for v in np.asarray(out["eigenvalues"])[:4]]}
         return dict(ms_step=ms_step, prof=prof, launches=launches, sssp_info=sssp_info, out=out, e2e_sec=e2e_sec,
-                    h2d=int(h2d), d2h=int(d2h), n=n_cells, d=n_pcs, nwp=n_wp)
+                    h2d=int(h2d), d2h=int(d2h), n=n_cells, d=n_pcs, nwp=n_wp, sanity=sanity)
 
     if world > 1:
         palantir_config.HOST_SPARSE_ON_ALL_RANKS = False      # rank 0 materialises the two sparse matrices
@@ -524,6 +536,9 @@ def run_gpu_arm(args):
             "bound": "hbm", "kernel": "adaptive_weights + symmetrize (merge_rows & co.)", "achieved": kb_bytes / kb_ms / 1e6,
             "peak": hbm_peak, "unit": "GB/s", "frac": kb_bytes / kb_ms / 1e6 / hbm_peak, "ms": kb_ms,
             "algorithmic": "N*(k+1)*12 B read + nnz*12 + 4*(N+1) B written", "peak_source": hbm_src},
+        "sanity": main["sanity"],
+        "memory_gib": {"peak_allocated_rank0": torch.cuda.max_memory_allocated() / 2 ** 30,
+                       "distance_rows_per_gpu": main["sssp_info"].get("sources", 0) * n * 8 / 2 ** 30},
         "stages_ms": {k: round(v, 3) for k, v in sorted(prof.items())},
         "stages_note": "max over ranks per stage",
         "lanczos": {k: v for k, v in (utils.LAST_INFO.get("lanczos") or {}).items() if k != "history"},

@@ -297,7 +297,16 @@ def sssp_cells(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = 
         call("pb200_cells_order", g.indptr, g.indices, n, key, P, cell, size_d, nb_d, arcs_d, order, inv, scratch,
              nbytes)
         del q
-        if int(lib.pb200_cells_overflowed(_native.stream_ptr())):
+        overflow = int(lib.pb200_cells_overflowed(_native.stream_ptr()))
+        if _dist.world()[1] > 1:
+            # the cells grow by first-come claims (within a margin), so two runs -- two ranks -- need not agree on
+            # them; every rank must use the same cells (its distance rows share their column order with the other
+            # ranks' in the reductions that follow): rank 0's are taken
+            flag = torch.tensor([overflow], dtype=I32, device=cell.device)
+            for t in (flag, cell, counts, arcs_d, order, inv):
+                _dist.broadcast_(t)
+            overflow = int(flag.item())
+        if overflow:
             return None
         counts_h = counts.cpu().numpy().astype(np.int64)
         size_h, nb_h = counts_h[:P + 1], counts_h[P + 1:]
