@@ -219,6 +219,11 @@ int pb200_maxmin_sampling(const double* data, long long n, int m, const long lon
                           unsigned int* done, void* stream);
 int pb200_gather_rows_f64(const double* a, int m, const long long* rows, long long nr, double* out, void* stream);
 
+/* ---- run_pca (utils.py:52-118: scanpy pca with zero_center=False = truncated SVD without centring) ---- */
+int pb200_pca_gram(const void* x, int is_f64, long long n, int g, long long ldx, double* C, void* stream);
+int pb200_pca_project(const void* x, int is_f64, long long n, int g, long long ldx, const double* V, int k,
+                      double* Y, void* stream);
+
 /* ---- reachability (networkx pass of _connect_graph, core.py:806-817) ---- */
 int pb200_graph_components(const int* indptr, const int* indices, long long n, int* label, void* stream);
 int pb200_count_other_label(const int* label, long long n, long long ref, int* count, void* stream);

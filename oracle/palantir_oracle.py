@@ -46,6 +46,19 @@ from sklearn.preprocessing import minmax_scale as _sk_minmax
 # ----------------------------------------------------------------------------
 
 
+def truncated_svd_pca(x, n_comps: int):
+    """What ``sc.pp.pca(ad, n_comps=n_comps, zero_center=False)`` computes (the call of run_pca, utils.py:92-104):
+    scanpy's zero_center=False branch is sklearn ``TruncatedSVD(n_components, random_state=0, algorithm="arpack")``
+    (scanpy/preprocessing/_pca/__init__.py, pinned scanpy>=1.6).  scanpy itself is not installed in the build
+    image, so this restatement is PARITY UNPINNED against the reference's own function; it is anchored on the
+    sklearn estimator scanpy delegates to.  Returns (X_pca, components, variance, variance_ratio)."""
+    from sklearn.decomposition import TruncatedSVD
+
+    svd = TruncatedSVD(n_components=n_comps, random_state=0, algorithm="arpack")
+    scores = svd.fit_transform(x)
+    return scores, svd.components_, svd.explained_variance_, svd.explained_variance_ratio_
+
+
 def knn_with_self(x: np.ndarray, n_neighbors: int, n_jobs: int = -1):
     """(dist, ind) of the ``n_neighbors`` nearest rows of ``x`` to every row of
     ``x`` (self included), as ``sklearn.neighbors.NearestNeighbors`` returns them.

@@ -37,7 +37,8 @@ class AnnDataLike:
         self.obs = pd.DataFrame(index=pd.Index(obs_names))
         g = 0 if X is None or len(X.shape) < 2 else X.shape[1]
         self.var_names = pd.Index(var_names) if var_names is not None else pd.Index([str(i) for i in range(g)])
-        self.obsm, self.obsp, self.uns, self.layers = {}, {}, {}, {}
+        self.var = pd.DataFrame(index=self.var_names)
+        self.obsm, self.obsp, self.uns, self.layers, self.varm = {}, {}, {}, {}, {}
 
     @property
     def obs_names(self) -> pd.Index:
@@ -46,3 +47,81 @@ class AnnDataLike:
     @property
     def n_obs(self) -> int:
         return len(self.obs.index)
+
+    @property
+    def n_vars(self) -> int:
+        return len(self.var_names)
+
+    # ---- on-disk round trip with the key layout an h5ad file keeps (anndata / h5py are not installed in the
+    # build image; with the real anndata use ad.write_h5ad / anndata.read_h5ad) ----
+    def write(self, path: str) -> None:
+        """One .npz holding X, obs / var columns, and every obsm / obsp / uns / layers / varm entry under
+        '<slot>/<key>'; DataFrames keep their columns ('<slot>/<key>@columns'), sparse matrices their CSR parts."""
+        from scipy.sparse import issparse
+
+        out = {"obs_names": np.asarray(self.obs_names, dtype=str), "var_names": np.asarray(self.var_names, dtype=str)}
+
+        def put(name, v):
+            if isinstance(v, pd.DataFrame):
+                out[name] = v.values
+                out[name + "@columns"] = np.asarray(v.columns, dtype=str)
+            elif isinstance(v, pd.Series):
+                out[name] = v.values
+            elif issparse(v):
+                c = v.tocsr()
+                out[name + "@csr_data"], out[name + "@csr_indices"] = c.data, c.indices
+                out[name + "@csr_indptr"], out[name + "@csr_shape"] = c.indptr, np.asarray(c.shape)
+            elif isinstance(v, dict):
+                for k2, v2 in v.items():
+                    put(name + "." + k2, v2)
+            else:
+                out[name] = np.asarray(v)
+            if name in out and out[name].dtype == object:
+                out[name] = out[name].astype(str)           # labels: stored as fixed-width text, as h5ad stores strings
+
+        if self.X is not None:
+            put("X", self.X)
+        for col in self.obs.columns:
+            put("obs/" + col, self.obs[col])
+        for col in self.var.columns:
+            put("var/" + col, self.var[col])
+        for slot in ("obsm", "obsp", "uns", "layers", "varm"):
+            for k, v in getattr(self, slot).items():
+                put(slot + "/" + k, v)
+        np.savez(path, **out)
+
+    @classmethod
+    def read(cls, path: str) -> "AnnDataLike":
+        from scipy.sparse import csr_matrix
+
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz", allow_pickle=False)
+        keys = list(z.keys())
+
+        def get(name):
+            if name + "@csr_data" in z:
+                return csr_matrix((z[name + "@csr_data"], z[name + "@csr_indices"], z[name + "@csr_indptr"]),
+                                  shape=tuple(z[name + "@csr_shape"]))
+            return z[name]
+
+        ad = cls(get("X") if ("X" in z or "X@csr_data" in z) else None, obs_names=z["obs_names"], var_names=z["var_names"])
+        if ad.X is None:
+            ad.obs = pd.DataFrame(index=pd.Index(z["obs_names"]))
+        names = {k.split("@")[0] for k in keys}
+        for name in sorted(names):
+            if "/" not in name:
+                continue
+            slot, key = name.split("/", 1)
+            val = get(name)
+            if name + "@columns" in z:
+                idx = ad.obs_names if slot == "obsm" else (ad.var_names if slot == "varm" else None)
+                val = pd.DataFrame(val, index=idx, columns=z[name + "@columns"])
+            if slot == "obs":
+                ad.obs[key] = val
+            elif slot == "var":
+                ad.var[key] = val
+            elif "." in key:                       # nested dict entry (uns['pca']['variance'] ...)
+                top, sub = key.split(".", 1)
+                getattr(ad, slot).setdefault(top, {})[sub] = val
+            else:
+                getattr(ad, slot)[key] = val
+        return ad

@@ -21,7 +21,7 @@ from . import _device as dv
 from . import config as palantir_config
 from .compat import is_anndata
 
-__all__ = ["compute_kernel", "diffusion_maps_from_kernel", "run_diffusion_maps",
+__all__ = ["run_pca", "compute_kernel", "diffusion_maps_from_kernel", "run_diffusion_maps",
            "determine_multiscale_space", "run_magic_imputation", "early_cell", "fallback_terminal_cell",
            "find_terminal_states", "CellNotFoundException"]
 
@@ -52,6 +52,145 @@ def _device_copy_of(kernel) -> Optional["dv.DeviceCSR"]:
         return None
     kern, fp = hit
     return kern if fp == _fingerprint(kernel) else None
+
+
+# ---------------------------------------------------------------------------
+# run_pca (reference utils.py:29-118): the step right before the path
+# ---------------------------------------------------------------------------
+PCA_ROW_BLOCK = 262144      # rows uploaded at a time (a sparse X is densified block by block)
+
+
+def _truncated_svd(X, n_comps: int):
+    """scanpy's ``sc.pp.pca(zero_center=False)`` = sklearn ``TruncatedSVD(algorithm="arpack")``: the leading
+    n_comps singular triplets of X (cells x genes, dense or scipy sparse) WITHOUT centring.  X^T X is accumulated
+    on the device in FP64 over row blocks, its G x G eigenproblem is solved on the host, the scores X V are
+    computed on the device; signs as sklearn's ``svd_flip(u_based_decision=False)`` (largest |entry| of every
+    component positive).  Returns (scores [n, k] in X's float type, components [k, g], variance, variance_ratio)."""
+    sparse_in = issparse(X)
+    if sparse_in:
+        X = X.tocsr()
+    n, g = X.shape
+    ftype = np.float64 if X.dtype == np.float64 else np.float32
+    dev_t = dv.F64 if ftype == np.float64 else dv.F32
+    C = dv.zeros((g, g), dv.F64)
+    colsum = dv.zeros((g,), dv.F64)
+
+    def block(r0):
+        r1 = min(n, r0 + PCA_ROW_BLOCK)
+        b = X[r0:r1].toarray() if sparse_in else np.asarray(X[r0:r1])
+        return dv.to_device(np.ascontiguousarray(b, dtype=ftype))
+
+    blocks = {}
+    for r0 in range(0, n, PCA_ROW_BLOCK):
+        xb = block(r0)
+        dv.call("pb200_pca_gram", xb, int(ftype == np.float64), xb.shape[0], g, g, C)
+        colsum += xb.sum(dim=0, dtype=torch.float64)
+        if n <= PCA_ROW_BLOCK:
+            blocks[r0] = xb                          # a single block stays on the device for the projection
+    Ch = C.cpu().numpy()
+    Ch = np.triu(Ch) + np.triu(Ch, 1).T            # the kernel fills the tiles on or above the diagonal
+    lam, vec = np.linalg.eigh(Ch)
+    order = np.argsort(lam)[::-1][:n_comps]
+    lam, vec = np.maximum(lam[order], 0.0), vec[:, order]
+    comps = vec.T.copy()                            # [k, g]
+    signs = np.sign(comps[np.arange(comps.shape[0]), np.argmax(np.abs(comps), axis=1)])
+    signs[signs == 0] = 1.0
+    comps *= signs[:, None]
+    Vd = dv.to_device(np.ascontiguousarray(comps.T))            # [g, k]
+    k = comps.shape[0]
+    scores = np.empty((n, k), dtype=ftype)
+    for r0 in range(0, n, PCA_ROW_BLOCK):
+        xb = blocks.get(r0)
+        if xb is None:
+            xb = block(r0)
+        yb = dv.empty((xb.shape[0], k), dv.F64)
+        for q0 in range(0, xb.shape[0], 1 << 21):                # grid.y limit of the projection kernel
+            q1 = min(xb.shape[0], q0 + (1 << 21))
+            dv.call("pb200_pca_project", xb[q0:q1], int(ftype == np.float64), q1 - q0, g, g, Vd, k, yb[q0:q1])
+        scores[r0:r0 + xb.shape[0]] = yb.to(dev_t).cpu().numpy()
+    mean = colsum.cpu().numpy() / n
+    var = lam / n - (comps @ mean) ** 2            # np.var of the scores: E[y^2] - E[y]^2 with y = X v
+    full_var = float((np.diag(Ch) / n - mean ** 2).sum())
+    return scores, comps, var, var / full_var
+
+
+def _slice_pca(ad, n_comps: int) -> None:
+    """Keep the first n_comps components of stored PCA results (reference utils.py:29-49)."""
+    if "X_pca" in ad.obsm:
+        ad.obsm["X_pca"] = ad.obsm["X_pca"][:, :n_comps]
+    if "pca" in ad.uns:
+        for key in ("variance", "variance_ratio"):
+            if key in ad.uns["pca"]:
+                ad.uns["pca"][key] = np.asarray(ad.uns["pca"][key])[:n_comps]
+        params = ad.uns["pca"].get("params")
+        if isinstance(params, dict) and "n_comps" in params:
+            params["n_comps"] = n_comps
+    if "PCs" in getattr(ad, "varm", {}):
+        ad.varm["PCs"] = ad.varm["PCs"][:, :n_comps]
+
+
+def _pca_into(ad, n_comps: int, mask=None) -> None:
+    """What ``sc.pp.pca(ad, n_comps, zero_center=False, mask_var=...)`` writes: obsm['X_pca'], varm['PCs'],
+    uns['pca'] = {params, variance, variance_ratio}."""
+    X = ad.X
+    if mask is not None:
+        X = X[:, np.asarray(mask, dtype=bool)]
+    scores, comps, var, ratio = _truncated_svd(X, n_comps)
+    ad.obsm["X_pca"] = scores
+    if not hasattr(ad, "varm") or ad.varm is None:
+        ad.varm = {}
+    if mask is not None:
+        pcs = np.zeros((ad.X.shape[1], comps.shape[0]), dtype=comps.dtype)
+        pcs[np.asarray(mask, dtype=bool)] = comps.T
+    else:
+        pcs = comps.T.copy()
+    ad.varm["PCs"] = pcs
+    ad.uns["pca"] = {"params": {"zero_center": False, "n_comps": int(comps.shape[0])},
+                     "variance": var, "variance_ratio": ratio}
+
+
+def run_pca(data, n_components: int = 300, use_hvg: bool = True, pca_key: str = "X_pca"):
+    """PCA of cells x genes data (reference utils.py:52-118).  A DataFrame is wrapped like the reference wraps it
+    in an AnnData; with ``use_hvg`` the components come from the genes flagged in ``var['highly_variable']``, 1000
+    of them first, cut where the cumulative variance ratio passes 0.85.  Returns (projections DataFrame,
+    variance ratio) and, for an AnnData, writes obsm[pca_key], varm['PCs'], uns['pca'] as scanpy does."""
+    from .compat import AnnDataLike
+
+    if isinstance(data, pd.DataFrame):
+        ad = AnnDataLike(data.values, obs_names=data.index, var_names=data.columns)
+        old_pca = None
+    else:
+        ad = data
+        old_pca = ad.obsm["X_pca"].copy() if (pca_key != "X_pca" and "X_pca" in ad.obsm) else None
+    n_obs, n_vars = ad.X.shape
+    if not use_hvg:
+        n_comps = min(n_components, n_obs - 1, n_vars - 1)
+        _pca_into(ad, n_comps)
+    else:
+        var = getattr(ad, "var", None)
+        if var is None or "highly_variable" not in var:
+            raise KeyError("highly_variable")         # scanpy: mask_var='highly_variable' needs ad.var['highly_variable']
+        mask = np.asarray(var["highly_variable"], dtype=bool)
+        l_n_comps = min(1000, n_obs - 1, n_vars - 1, int(mask.sum()) - 1)
+        _pca_into(ad, l_n_comps, mask)
+        try:
+            n_comps = np.where(np.cumsum(ad.uns["pca"]["variance_ratio"]) > 0.85)[0][0]
+        except IndexError:
+            n_comps = n_components
+        n_comps = min(n_comps, n_obs - 1, n_vars - 1)
+        if n_comps < l_n_comps:
+            _slice_pca(ad, n_comps)
+        elif n_comps > l_n_comps:
+            _pca_into(ad, n_comps, mask)
+    pca_projections = pd.DataFrame(ad.obsm["X_pca"], index=ad.obs_names)
+    variance_ratio = ad.uns["pca"]["variance_ratio"]
+    if is_anndata(data) and pca_key != "X_pca":
+        data.obsm[pca_key] = ad.obsm["X_pca"]
+        if old_pca is not None:
+            data.obsm["X_pca"] = old_pca
+        else:
+            del data.obsm["X_pca"]
+    return pca_projections, variance_ratio
 
 
 def _knn_table(values: np.ndarray, n_neighbors: int):

@@ -693,6 +693,91 @@ def test_magic_imputation_at_scale_with_chunks(pb, monkeypatch):
     assert np.max(np.abs(got2 - got[:, :64])) <= 2e-6
 
 
+# ------------------------------------------------------------------ upstream / downstream of the path
+@pytest.mark.parametrize("dtype,sparse_in", [(np.float64, False), (np.float32, False), (np.float64, True)])
+def test_run_pca_vs_truncated_svd(pb, po, dtype, sparse_in, monkeypatch):
+    """run_pca (utils.py:52-118) against sklearn's TruncatedSVD(arpack), which scanpy's zero_center=False path
+    calls (scanpy is not installed here: see oracle.truncated_svd_pca).  Scores / components up to sign."""
+    from palantir_b200.compat import AnnDataLike
+
+    rng = np.random.default_rng(4)
+    n, g, k = 3000, 180, 25
+    lat = rng.normal(size=(n, 12)) * np.linspace(4, 1, 12)
+    x = np.maximum(lat @ rng.normal(size=(12, g)) + 0.3 * rng.normal(size=(n, g)) + 1.0, 0).astype(dtype)
+    xin = csr_matrix(x) if sparse_in else x
+    monkeypatch.setattr(pb.utils, "PCA_ROW_BLOCK", 1024)                 # several row blocks
+    ad = AnnDataLike(xin, obs_names=[f"c{i}" for i in range(n)])
+    proj, ratio = pb.utils.run_pca(ad, n_components=k, use_hvg=False)
+    scores, comps, var, vr = po.truncated_svd_pca(xin, k)
+    tol = 1e-8 if dtype == np.float64 else 2e-3
+    assert proj.shape == (n, k) and list(proj.index) == list(ad.obs_names) and proj.values.dtype == dtype
+    sgn = np.sign(np.sum(proj.values * scores, axis=0))
+    assert np.max(np.abs(proj.values * sgn - scores)) <= tol * np.abs(scores).max()
+    assert np.max(np.abs(ratio - vr)) <= tol and np.max(np.abs(ad.uns["pca"]["variance"] - var)) <= tol * var.max()
+    assert np.max(np.abs(ad.varm["PCs"].T * sgn[:, None] - comps)) <= max(tol, 1e-6)
+    if dtype == np.float64 and not sparse_in:
+        assert np.array_equal(sgn, np.ones(k))                            # sklearn's svd_flip convention reproduced
+    # DataFrame input, other key, highly-variable-gene path with the 85 % cut
+    ad2 = AnnDataLike(x, obs_names=ad.obs_names)
+    ad2.var["highly_variable"] = np.arange(g) % 3 != 0
+    ad2.obsm["X_pca"] = np.zeros((n, 2))
+    p2, r2 = pb.utils.run_pca(ad2, n_components=k, use_hvg=True, pca_key="X_hvg")
+    assert np.array_equal(ad2.obsm["X_pca"], np.zeros((n, 2))) and ad2.obsm["X_hvg"].shape == p2.shape
+    _, _, _, vr_full = po.truncated_svd_pca(x[:, ad2.var["highly_variable"].values], min(1000, n - 1, int(ad2.var["highly_variable"].sum()) - 1))
+    want = int(np.where(np.cumsum(vr_full) > 0.85)[0][0])
+    assert p2.shape[1] == want and ad2.varm["PCs"].shape == (g, want)
+    assert np.all(ad2.varm["PCs"][~ad2.var["highly_variable"].values] == 0)
+    p3, r3 = pb.utils.run_pca(pd.DataFrame(x, index=ad.obs_names), n_components=7, use_hvg=False)
+    assert p3.shape == (n, 7) and np.max(np.abs(np.abs(p3.values) - np.abs(proj.values[:, :7]))) <= tol * np.abs(scores).max()
+
+
+@pytest.mark.parametrize("save_as_df", [True, False])
+def test_results_survive_the_on_disk_round_trip(pb, names1500, tmp_path, save_as_df):
+    """The AnnData keys the path writes (core.py:237-247; north_star) written to disk and read back: with
+    SAVE_AS_DF the fate probabilities are a DataFrame whose columns are the terminal cells, without it an array
+    plus uns['palantir_fate_probabilities_columns'].  anndata / h5py are not installed in the build image, so the
+    stand-in's .npz container with the same key layout is used; with the real anndata the same test goes through
+    write_h5ad / read_h5ad."""
+    from palantir_b200.compat import AnnDataLike
+
+    z = golden("palantir_n1500_wp200.npz")
+    names = names1500
+    ad = AnnDataLike(np.zeros((1500, 3)), obs_names=names)
+    ad.obsm["DM_EigenVectors_multiscaled"] = z["ms"]
+    pb.core.run_palantir(ad, names[int(z["early"])], terminal_states=list(names[z["terminals"]]), num_waypoints=200,
+                         save_as_df=save_as_df)
+    path = str(tmp_path / "ad.npz")
+    ad.write(path)
+    back = AnnDataLike.read(path)
+    assert np.array_equal(back.obs["palantir_pseudotime"].values, ad.obs["palantir_pseudotime"].values)
+    assert np.max(np.abs(back.obs["palantir_pseudotime"].values - z["pseudotime"])) <= 1e-10
+    assert np.array_equal(back.obs["palantir_entropy"].values, ad.obs["palantir_entropy"].values)
+    assert list(back.uns["palantir_waypoints"]) == list(ad.uns["palantir_waypoints"])
+    fp = back.obsm["palantir_fate_probabilities"]
+    if save_as_df:
+        assert isinstance(fp, pd.DataFrame) and list(fp.columns) == list(names[z["fate_columns"]])
+        assert "palantir_fate_probabilities_columns" not in back.uns
+        vals = fp.values
+    else:
+        assert isinstance(fp, np.ndarray)
+        assert list(back.uns["palantir_fate_probabilities_columns"]) == list(names[z["fate_columns"]])
+        vals = fp
+    assert np.max(np.abs(vals - z["fate_probs"])) <= 1e-9
+    try:
+        import anndata
+    except ImportError:
+        return
+    real = anndata.AnnData(np.zeros((1500, 3)))
+    real.obs_names = names
+    real.obsm["DM_EigenVectors_multiscaled"] = z["ms"]
+    pb.core.run_palantir(real, names[int(z["early"])], terminal_states=list(names[z["terminals"]]), num_waypoints=200,
+                         save_as_df=save_as_df)
+    real.write_h5ad(str(tmp_path / "ad.h5ad"))
+    again = anndata.read_h5ad(str(tmp_path / "ad.h5ad"))
+    assert np.max(np.abs(again.obs["palantir_pseudotime"].values - z["pseudotime"])) <= 1e-10
+    assert np.max(np.abs(np.asarray(again.obsm["palantir_fate_probabilities"]) - z["fate_probs"])) <= 1e-9
+
+
 # ------------------------------------------------------------------ benchmark-size properties
 def test_properties_at_benchmark_scale(pb):
     """Config 2 (100k cells x 50 PCs, 1200 waypoints): properties that hold at any size."""

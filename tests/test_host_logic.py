@@ -371,3 +371,49 @@ def test_every_abi_entry_point_is_documented():
     assert len(names) > 60
     missing = [n for n in names if n not in doc and n.rstrip("12") not in doc]
     assert not missing, missing
+
+
+def test_install_aliases_the_package_as_palantir():
+    """the implementation is importable as `palantir` (the reference itself is not installed here)."""
+    import importlib
+    import subprocess
+
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import palantir_b200\n"
+        "m = palantir_b200.install()\n"
+        "import palantir\n"
+        "from palantir.utils import run_diffusion_maps, determine_multiscale_space, run_magic_imputation, run_pca\n"
+        "from palantir.core import run_palantir\n"
+        "from palantir.presults import PResults\n"
+        "import palantir.config\n"
+        "assert palantir is palantir_b200 and run_palantir is palantir_b200.core.run_palantir\n"
+        "assert palantir.run_palantir is run_palantir and palantir.config.SAVE_AS_DF is True\n"
+        "print('ok')\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
+def test_install_patches_an_installed_reference(monkeypatch):
+    """With the reference importable, install() re-binds exactly the functions of the path and leaves the rest."""
+    import types
+
+    import palantir_b200
+
+    ref = types.ModuleType("palantir")
+    ref.utils, ref.core = types.ModuleType("palantir.utils"), types.ModuleType("palantir.core")
+    ref.presults, ref.validation = types.ModuleType("palantir.presults"), types.ModuleType("palantir.validation")
+    ref.plot = types.ModuleType("palantir.plot")
+    sentinel = object()
+    ref.utils.run_diffusion_maps = ref.utils.run_density = sentinel
+    ref.core.run_palantir = ref.run_palantir = sentinel
+    ref.plot.plot_palantir_results = sentinel
+    for name, mod in (("palantir", ref), ("palantir.utils", ref.utils), ("palantir.core", ref.core),
+                      ("palantir.presults", ref.presults), ("palantir.validation", ref.validation)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    out = palantir_b200.install()
+    assert out is ref and ref.__pb200_installed__
+    assert ref.utils.run_diffusion_maps is palantir_b200.utils.run_diffusion_maps
+    assert ref.core.run_palantir is palantir_b200.core.run_palantir and ref.run_palantir is palantir_b200.core.run_palantir
+    assert ref.utils.run_density is sentinel and ref.plot.plot_palantir_results is sentinel      # off the path: untouched
+    assert ref.presults.PResults is palantir_b200.PResults
