@@ -202,6 +202,10 @@ int pb200_lanczos_steps_pro(const int* indptr, const int* indices, const double*
                             int j0, int nsteps, double* alpha, double* beta, double* w, double* h, double* partial,
                             double* tmp, double* om, long long omstride, int* gate, int* counters, double eps,
                             double thresh, void* stream);
+/* Arnoldi steps for a kernel that is not symmetric (utils.py:477-484 takes any kernel): H column-major [ldh][mcap] */
+int pb200_arnoldi_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                        double* V, long long ldv, int j0, int nsteps, double* H, int ldh, double* w, double* h,
+                        double* h2, double* partial, double* tmp, void* stream);
 int pb200_ritz_vectors(const double* V, long long ldv, int m, const double* Y, int kk, const double* scale,
                        double* U, long long n, void* stream);
 /* unit-L2 columns.  scratch: partial[kk * (n/4096+1)], sumsq[kk] */

@@ -638,6 +638,58 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
     return theta, U, info
 
 
+def arnoldi_topk(kern: DeviceCSR, tvals: torch.Tensor, start: torch.Tensor, k: int, tol: float = 1e-10,
+                 batch: int = 20, max_basis: Optional[int] = None):
+    """Largest-magnitude k eigenpairs of the row-stochastic T = D^-1 K of a kernel that is NOT symmetric (the
+    reference hands any kernel to ARPACK's general solver, utils.py:484) by Arnoldi with two Gram-Schmidt passes,
+    un-restarted.  Returns (real parts of the eigenvalues, descending [k]; U [n, k] = real parts of the Ritz
+    vectors, unit L2 columns; info) -- the reference keeps the real parts too (utils.py:485-486)."""
+    n, nnz = kern.n, kern.nnz
+    if not (0 < k < n):
+        raise ValueError("need 0 < k < n eigenpairs")
+    if max_basis is None:
+        max_basis = int(min(n - 1, max(4 * k + 40, min(1024, (20 << 30) // (8 * n)))))
+    ld = n
+    nblk = n // 2048 + 1
+    V = empty((max_basis + 1, ld), F64)
+    ldh = max_basis + 1
+    H = zeros((max_basis, ldh), F64)                         # column-major: H[j] is column j
+    w, h, h2 = empty((n,), F64), empty((max_basis + 1,), F64), empty((max_basis + 1,), F64)
+    partial = empty(((max_basis + 1) * nblk,), F64)
+    tmp = empty((1,), F64)
+    call("pb200_lanczos_init", start, n, V, None, partial, tmp)
+    m, info = 0, {"converged": False, "solver": "arnoldi"}
+    lam = yv = None
+    while m < max_basis:
+        steps = min(batch, max_basis - m)
+        with stage("lanczos_steps"):
+            call("pb200_arnoldi_steps", kern.indptr, kern.indices, tvals, n, nnz, V, ld, m, steps, H, ldh, w, h, h2,
+                 partial, tmp)
+        m += steps
+        if m < k + 1 and m < max_basis:
+            continue
+        Hh = H[:m].cpu().numpy().T                           # [ldh, m]: rows 0..m
+        vals, vecs = np.linalg.eig(Hh[:m, :m])
+        order = np.argsort(-np.abs(vals))[:k]
+        resid = np.abs(Hh[m, m - 1]) * np.abs(vecs[m - 1, order])
+        lam, yv = vals[order], vecs[:, order]
+        info.update(steps=m, max_resid=float(resid.max()))
+        if np.all(resid <= tol * np.maximum(np.abs(lam), 1e-3)) or Hh[m, m - 1] <= 1e-14:
+            info["converged"] = True
+            break
+    if not info["converged"]:
+        raise RuntimeError(f"Arnoldi did not converge in {m} steps (max residual {info.get('max_resid')})")
+    lam_r = np.real(lam)
+    srt = np.argsort(-lam_r)
+    lam_r, yr = lam_r[srt], np.ascontiguousarray(np.real(yv[:, srt]))
+    U = empty((n, k), F64)
+    call("pb200_ritz_vectors", V, ld, m, to_device(yr), k, None, U, n)
+    part2 = empty((k * (n // 4096 + 1),), F64)
+    sumsq = empty((k,), F64)
+    call("pb200_normalize_columns", U, n, k, part2, sumsq)
+    return lam_r, U, info
+
+
 def check_symmetric(kern: DeviceCSR, tol: float = 1e-12) -> bool:
     flag = empty((1,), I32)
     call("pb200_csr_is_symmetric", kern.indptr, kern.indices, kern.data, kern.n, tol, flag)

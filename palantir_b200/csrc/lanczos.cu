@@ -518,6 +518,13 @@ __global__ void lanczos_fix_alpha_kernel(const double* __restrict__ h, int j, do
   if (threadIdx.x == 0 && *gate) alpha[j] += h[j];
 }
 
+// Arnoldi bookkeeping: H[0..j][j] = h + h2 (two Gram-Schmidt passes), H[j+1][j] = sqrt(nrm2); H column-major, ldh rows
+__global__ void arnoldi_store_kernel(const double* __restrict__ h, const double* __restrict__ h2, int j,
+                                     const double* __restrict__ nrm2, double* __restrict__ H, int ldh) {
+  for (int c = threadIdx.x; c <= j; c += blockDim.x) H[(long long)j * ldh + c] = h[c] + h2[c];
+  if (threadIdx.x == 0) H[(long long)j * ldh + j + 1] = sqrt(*nrm2);
+}
+
 __global__ void vec_mul_kernel(const double* __restrict__ a, const double* __restrict__ b,
                                double* __restrict__ out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -833,6 +840,38 @@ int pb200_lanczos_steps_pro(const int* indptr, const int* indices, const double*
     PB_CHECK_LAUNCH("reduce_partials_kernel(nrm2, gated)");
     scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V + (long long)(j + 1) * ldv,
                                                          V32 ? V32 + (long long)(j + 1) * ldv : nullptr, n, beta + j + 1);
+    PB_CHECK_LAUNCH("scale_by_norm_kernel");
+  }
+  return 0;
+}
+
+// Arnoldi steps j = j0 .. j0+nsteps-1 for a general (non-symmetric) CSR matrix, e.g. T = D^-1 K of a kernel that
+// is not symmetric (utils.py:477-484 accepts any kernel): w = A v_j, two classical Gram-Schmidt passes against
+// V[0..j], H[:, j] (column-major, ldh >= mcap + 1 rows), v_{j+1} = w / |w|.  Scratch: w[n], h[mcap], h2[mcap],
+// partial[mcap * div_up(n, 2048)], tmp[1].
+int pb200_arnoldi_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                        double* V, long long ldv, int j0, int nsteps, double* H, int ldh, double* w, double* h,
+                        double* h2, double* partial, double* tmp, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = div_up(n, VCHUNK);
+  for (int j = j0; j < j0 + nsteps; ++j) {
+    const int m = j + 1;
+    int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st);
+    if (rc) return rc;
+    for (int pass = 0; pass < 2; ++pass) {
+      double* hh = pass ? h2 : h;
+      multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V, ldv, m, w, n, partial);
+      PB_CHECK_LAUNCH("multi_dot_kernel(arnoldi)");
+      reduce_partials_kernel<<<m, 256, 0, st>>>(partial, nblk, m, hh, nullptr);
+      PB_CHECK_LAUNCH("reduce_partials_kernel(arnoldi)");
+      multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * m, st>>>(V, ldv, m, hh, w, n);
+      PB_CHECK_LAUNCH("multi_axpy_kernel(arnoldi)");
+    }
+    rc = nrm2_into(w, n, partial, tmp, st);
+    if (rc) return rc;
+    arnoldi_store_kernel<<<1, 256, 0, st>>>(h, h2, j, tmp, H, ldh);
+    PB_CHECK_LAUNCH("arnoldi_store_kernel");
+    scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V + (long long)(j + 1) * ldv, nullptr, n, nullptr);
     PB_CHECK_LAUNCH("scale_by_norm_kernel");
   }
   return 0;

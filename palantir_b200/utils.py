@@ -248,21 +248,24 @@ def _diffusion_maps_device(kern: dv.DeviceCSR, n_components: int, seed, t_home: 
     """(T values, eigenvalues, eigenvectors) on the device.  With ``t_home`` (a list) the copy of T
     to the host is started before the eigensolver and its finisher appended to the list."""
     n = kern.n
-    if not kern.symmetric and not dv.check_symmetric(kern):
-        raise dv.NotSymmetricError(
-            "diffusion_maps_from_kernel on B200 runs a symmetric Lanczos solver and needs a symmetric "
-            "kernel (compute_kernel always produces one)")
+    symmetric = kern.symmetric or dv.check_symmetric(kern)
     tvals, svals, dis, dsq = dv.transition_and_symmetric(kern)
-    # same RNG use as the reference (utils.py:482-483); the start vector is mapped to the
-    # symmetric problem: K_m(T, v0) = D^-1/2 K_m(S, D^1/2 v0)
+    # same RNG use as the reference (utils.py:482-483)
     np.random.seed(seed)
     v0 = np.random.rand(n)
-    start = dv.empty((n,), dv.F64)
-    dv.call("pb200_vec_mul", dv.to_device(v0), dsq, start, n)
     if t_home is not None:
         t_home.append(dv.csr_to_host_async(kern, tvals))
-    with dv.stage("eigensolver"):
-        lam, U, info = dv.lanczos_topk(kern, svals, dis, start, n_components)
+    if symmetric:
+        # symmetric Lanczos on S = D^-1/2 K D^-1/2; the start vector is mapped to the symmetric problem:
+        # K_m(T, v0) = D^-1/2 K_m(S, D^1/2 v0)
+        start = dv.empty((n,), dv.F64)
+        dv.call("pb200_vec_mul", dv.to_device(v0), dsq, start, n)
+        with dv.stage("eigensolver"):
+            lam, U, info = dv.lanczos_topk(kern, svals, dis, start, n_components)
+    else:
+        # a kernel that is not symmetric (the reference takes any matrix, utils.py:477-484): Arnoldi on T itself
+        with dv.stage("eigensolver"):
+            lam, U, info = dv.arnoldi_topk(kern, tvals, dv.to_device(v0), n_components)
     from . import _dist
 
     if _dist.world()[1] > 1:

@@ -177,6 +177,37 @@ def test_diffusion_maps_from_kernel_reference_tests(pb):
     assert pb.utils.determine_multiscale_space(r).shape[0] == 50
 
 
+def test_kernel_that_is_not_symmetric(pb):
+    """diffusion_maps_from_kernel accepts any kernel (utils.py:477-484 hands T to ARPACK's general solver): a
+    directed kNN affinity matrix goes through the Arnoldi path; real parts of the leading eigenpairs as in the
+    reference (utils.py:485-495), compared with scipy's eigs run to convergence."""
+    from scipy.sparse.linalg import eigs
+    from sklearn.neighbors import NearestNeighbors
+
+    rng = np.random.default_rng(8)
+    pts = rng.normal(size=(700, 3)) * np.array([4.0, 1.0, 0.3])
+    g = NearestNeighbors(n_neighbors=12).fit(pts).kneighbors_graph(pts, mode="distance")
+    g.data = np.exp(-g.data / np.median(g.data))              # W only, no W + W^T: not symmetric
+    k = csr_matrix(g)
+    assert abs(k - k.T).max() > 0.1
+    res = pb.utils.diffusion_maps_from_kernel(k, n_components=6, seed=0)
+    assert pb.utils.LAST_INFO["lanczos"]["solver"] == "arnoldi"
+    deg = np.asarray(k.sum(axis=1)).ravel()
+    t = csr_matrix((1.0 / deg)[:, None] * k.toarray())
+    assert abs(res["T"] - t).max() < 1e-14
+    w, v = eigs(t, 6, tol=1e-13, maxiter=20000, v0=np.ones(700))
+    order = np.argsort(-np.real(w))
+    w, v = np.real(w[order]), np.real(v[:, order])
+    assert np.max(np.abs(res["EigenValues"].values - w)) < 1e-8
+    got = res["EigenVectors"].values
+    assert np.allclose(np.linalg.norm(got, axis=0), 1.0)
+    for c in range(6):
+        if np.abs(np.imag(eigs(t, 6, tol=1e-13, maxiter=20000, v0=np.ones(700))[0][order][c])) > 0:
+            continue                                           # complex pair: the real part of a vector is not unique
+        ref = v[:, c] / np.linalg.norm(v[:, c])
+        assert min(np.abs(got[:, c] - ref).max(), np.abs(got[:, c] + ref).max()) < 1e-6
+
+
 def test_kernel_edited_in_place_is_uploaded_again(pb):
     """compute_kernel leaves a device copy on the matrix it returns; editing the matrix in place must
     not let diffusion_maps_from_kernel use the stale copy."""
