@@ -6,7 +6,7 @@
 One "step" is one pass of the hot path (run_diffusion_maps -> determine_multiscale_space ->
 run_palantir) over one synthetic branching-trajectory matrix.  The default configuration is
 BASELINE.json config 3 (1,000,000 cells x 100 PCs, knn 30, 10 diffusion components, 1200 waypoints);
---config c2 is config 2 (100 k x 50), c4 config 4 (4 M x 50, 5000 waypoints: meant for 8 GPUs), c5
+--config c1 is the tutorial-sized case (4142 x 100, 500 waypoints), c2 config 2 (100 k x 50), c4 config 4 (4 M x 50, 5000 waypoints: meant for 8 GPUs), c5
 config 5 (run_magic_imputation, t = 3, 1 M cells x 2000 genes).
 
 `value`   : cells/s with the PCA matrix already resident in HBM and all results left there
@@ -47,6 +47,7 @@ UNIT = "cells/s"
 KNN, NCOMP = 30, 10
 CONFIGS = {
     # name: (cells, PCs, waypoints)
+    "c1": (4_142, 100, 500),          # the size of the reference's tutorial data set (config 1; synthetic stand-in)
     "c2": (100_000, 50, 1200),
     "c3": (1_000_000, 100, 1200),
     "c4": (4_000_000, 50, 5000),
@@ -58,7 +59,7 @@ def _metric(cfg):
     if cfg == "c5":
         return "cells/s, run_magic_imputation t=3 at 1M cells x 2000 genes"
     n = CONFIGS[cfg][0]
-    label = {100_000: "100k", 1_000_000: "1M", 4_000_000: "4M"}[n]
+    label = {4_142: "4142", 100_000: "100k", 1_000_000: "1M", 4_000_000: "4M"}[n]
     return f"cells/s, run_diffusion_maps + determine_multiscale_space + run_palantir at {label} cells"
 
 
@@ -567,7 +568,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cells", type=int, default=0, help="override the configuration's cell count")
     ap.add_argument("--pcs", type=int, default=0, help="override the configuration's PC count")
     ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end (public API) measurement")

@@ -162,6 +162,39 @@ def test_c3_results_are_sane(pb, c3):
         assert fp[p].max() > 0.9
 
 
+def test_c1_sized_full_run_vs_oracles(pb, po):
+    """Config 1's size (4142 cells x 100 PCs, 500 waypoints: the reference's tutorial data set, here the synthetic
+    generator since the bundled h5ad is not in the checkout) through the public API: against the converged oracle
+    at the north_star tolerances, and against the reference AS SHIPPED (ARPACK tol 1e-4) for the eigenvalues, as
+    the reference's own test does (tests/test_utils_diffusion_maps_from_kernel.py:44-52, atol 1e-4)."""
+    from palantir_b200.datasets import synth_branching, synth_names
+
+    n, d, nwp = 4142, 100, 500
+    x, info = synth_branching(n, d, seed=0)
+    names = synth_names(n)
+    term = list(info["terminals"].values())
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = pb.utils.run_diffusion_maps(pd.DataFrame(x, index=names), n_components=10, knn=30,
+                                          kernel_backend="sklearn")
+        ms = pb.utils.determine_multiscale_space(res)
+        pr = pb.core.run_palantir(ms, names[info["early"]], terminal_states=list(names[term]), num_waypoints=nwp)
+        o = po.run_diffusion_maps(x, 10, 30, tol=1e-12)
+        asis = po.run_diffusion_maps(x, 10, 30)
+        oms = po.multiscale_space(o["EigenVectors"], o["EigenValues"])
+        op = po.run_palantir(oms, info["early"], terminal=term, num_waypoints=nwp)
+    assert np.array_equal(res["kernel"].indices, o["kernel"].indices)
+    assert np.max(np.abs(res["kernel"].data - o["kernel"].data) / o["kernel"].data) <= 1e-12
+    ev = res["EigenValues"].values
+    assert np.max(np.abs(ev - o["EigenValues"]) / np.abs(o["EigenValues"])) <= 1e-5
+    assert np.allclose(ev, asis["EigenValues"], atol=1e-4)
+    assert subspace_angles(res["EigenVectors"].values, o["EigenVectors"]).max() < 1e-4
+    assert ms.shape == oms.shape
+    assert list(names.get_indexer(pr.waypoints)) == list(op["waypoints"])
+    assert np.max(np.abs(pr.pseudotime.values - op["pseudotime"])) <= 1e-4
+    assert spearmanr(pr.pseudotime.values, op["pseudotime"])[0] > 0.999
+    assert np.max(np.abs(pr.branch_probs.values - op["fate_probs"])) <= 1e-4
+
+
 def test_c2_full_run_vs_tight_oracle(pb, po):
     """Config 2 (100 k cells x 50 PCs, 1200 waypoints) through the public API against the converged oracle
     (ARPACK tol 1e-12; the reference as shipped stops at 1e-4 and is itself ~1e-3 rad from its converged
