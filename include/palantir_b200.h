@@ -94,6 +94,7 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
 /* TF32 tensor peak probe: blocks CTAs x iters bare tcgen05.mma.kind::tf32 128x128x8 instructions (262144 FLOP each);
  * timed by the caller; the roofline denominator of pb200_knn_candidates_tc (bench.py) */
 int pb200_tf32_peak(int blocks, int iters, void* stream);
+int pb200_tf32_peak_rot(int blocks, int iters, int rot, void* stream);   /* rot 0 / 1 / 3: 1 / 2 / 4 accumulators */
 int pb200_knn_flagged_rows(const unsigned char* flag, int nq, int* rows_out, int* counter, void* stream);
 
 /* Exact FP64 brute force for the listed rows.  scratch: n_ctas * n doubles. */

@@ -627,7 +627,7 @@ __global__ void knn_prep_tc_kernel(const T* __restrict__ x, long long n, int d, 
 // roofline denominator of the candidate kernel is this kernel's measured FLOP/s (MEASURED_PEAKS.json has no
 // TF32 figure).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, int rot) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ uint64_t done_bar;
   __shared__ uint32_t tmem_base;
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
   if (warp == 1 && tc_elect_one()) {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     const uint64_t bdesc = tc_smem_desc(smem_u32(b));
-    for (int i = 0; i < iters; ++i) tc_mma_tf32_ts(tmem + (uint32_t)(i & 3) * TC_BN, tmem + 504u, bdesc, idesc, i >= 4 ? 1u : 0u);
+    for (int i = 0; i < iters; ++i) tc_mma_tf32_ts(tmem + (uint32_t)(i & rot) * TC_BN, tmem + 504u, bdesc, idesc, i >= 4 ? 1u : 0u);
     tc_commit(&done_bar);
   }
   if (warp == 1) mbar_wait(&done_bar, 0);
@@ -738,11 +738,15 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   return 0;
 }
 
+int pb200_tf32_peak_rot(int blocks, int iters, int rot, void* stream);
 // TF32 tensor peak probe (tf32_peak_kernel): `blocks` CTAs, `iters` 128x128x8 MMAs each = blocks * iters * 262144 FLOP.
-int pb200_tf32_peak(int blocks, int iters, void* stream) {
+int pb200_tf32_peak(int blocks, int iters, void* stream) { return pb200_tf32_peak_rot(blocks, iters, 3, stream); }
+
+// rot = 0, 1 or 3: the MMAs rotate over 1, 2 or 4 accumulators (dependent-accumulation probe)
+int pb200_tf32_peak_rot(int blocks, int iters, int rot, void* stream) {
   if (blocks < 1 || iters < 4) { set_error_msg("pb200_tf32_peak: need blocks >= 1, iters >= 4"); return -1; }
   PB_CHECK(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_HALF + 1024));
-  tf32_peak_kernel<<<blocks, 128, TC_HALF + 1024, (cudaStream_t)stream>>>(iters);
+  tf32_peak_kernel<<<blocks, 128, TC_HALF + 1024, (cudaStream_t)stream>>>(iters, rot);
   PB_CHECK_LAUNCH("tf32_peak_kernel");
   return 0;
 }
