@@ -342,6 +342,7 @@ def sssp_cells(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = 
     it_cell = np.repeat(kc, nb_h[kc])
     it_src = np.arange(len(it_cell)) - np.repeat(np.cumsum(nb_h[kc]) - nb_h[kc], nb_h[kc])
     it_out = toff[it_cell] + it_src * size_h[it_cell]
+    kc_items = it_cell
     sj = np.flatnonzero(src_interior)
     it_cell = np.concatenate([it_cell, src_cell[sj]])
     it_src = np.concatenate([it_src, src_local[sj]])
@@ -352,10 +353,32 @@ def sssp_cells(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[float] = 
         cell2, nint = empty((n,), I32), empty((n,), I32)
         call("pb200_cells_relabel", g.indptr, g.indices, g.data, n, order, inv, cell, indptr2, indices2, wts2, cell2,
              nint, scratch, nbytes)
-        sel = np.argsort(it_cell, kind="stable")          # items of a cell next to each other: its arcs stay in L2 / L1
+        # the tables do not depend on the sources: with several ranks every rank computes the cells of a contiguous
+        # range (balanced by boundary vertices x arcs) and the ranges are exchanged; the rows of a rank's own interior
+        # sources are always its own
+        rank, world = _dist.world()
+        n_tab = len(kc_items)
+        mine = np.ones(len(it_cell), dtype=bool)
+        cut_cells = None
+        if world > 1 and n_tab > 0:
+            work = np.cumsum(nb_h[kc] * arcs_h[kc])
+            cut_cells = np.concatenate([[0], np.searchsorted(work, work[-1] * np.arange(1, world) / world, side="right"),
+                                        [len(kc)]])
+            own_cells = np.zeros(P + 1, dtype=bool)
+            own_cells[kc[cut_cells[rank]:cut_cells[rank + 1]]] = True
+            mine[:n_tab] = own_cells[it_cell[:n_tab]]
+        sel = np.flatnonzero(mine)
+        sel = sel[np.argsort(it_cell[sel], kind="stable")]   # items of a cell next to each other: its arcs stay in L2 / L1
         call("pb200_cells_local_sssp", indptr2, nint, indices2, wts2, cells_d, dv.to_device(it_cell[sel].astype(np.int32)),
              dv.to_device(it_src[sel].astype(np.int32)), dv.to_device(it_out[sel].astype(np.int64)), int(sel.size),
              float(delta) * CELL_LOCAL_DELTA, T)
+        if cut_cells is not None:
+            for r in range(world):
+                a, b = cut_cells[r], cut_cells[r + 1]
+                if b > a:
+                    lo = int(toff[kc[a]])
+                    hi = int(toff[kc[b - 1]] + tsz[kc[b - 1]])
+                    torch.distributed.broadcast(T[lo:hi], src=r)
     with stage("sssp_overlay"):
         src_toff = dv.to_device(src_toff_h)
         pos_ov, ov_pos = empty((n,), I32), empty((max(1, n_ov),), I32)
