@@ -236,14 +236,13 @@ int pb200_point_dists_expanded(const double* data, long long n, int m, long long
 
 /* ---- multi-source shortest paths: scipy.sparse.csgraph.dijkstra(directed=False), core.py:362 ---- */
 int pb200_sssp_num_ctas(int n_sources);
-int pb200_sssp_set_ctas_per_sm(int c);
-int pb200_sssp_set_variant(int v);
-/* 1 if a near list of the shared-memory-table variant (12) outgrew its buffer since the last call; clears the flag */
+/* 1 if a work list of the shared-memory-table kernel outgrew its buffer since the last call; clears the flag */
 int pb200_sssp_overflowed(void* stream);
-/* D[n_sources][n]; scratch: q[n_ctas*3*n] int, bits[n_ctas*3*ceil(n/32)] uint32; stats [n_sources][3] or NULL */
+/* D[n_sources][n]; scratch: q[n_ctas*3*n] int, bits[n_ctas*3*ceil(n/32)] uint32; stats [n_sources][3] or NULL;
+ * exact_membership != 0: global bitmaps instead of shared-memory tag tables (the re-run after an overflow) */
 int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
-                     int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,
-                     void* stream);
+                     int n_sources, double delta, int exact_membership, double* D, int* q, unsigned int* bits,
+                     long long* stats, void* stream);
 
 /* Arc-record form of the same search: arcs[nnz + 64] of {int v; int indptr[v]; double w} (16 B each); work lists
  * hold (vertex, row start) pairs.  scratch: q[n_ctas*3*n] int pairs, bits[n_ctas*3*ceil(n/32)] uint32 with

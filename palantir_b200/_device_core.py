@@ -217,18 +217,14 @@ def sssp_per_source(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[floa
     stats = zeros((S, 3), I64) if want_stats else None
     nwords = (n + 31) // 32
     def exact_rerun():
-        # both default kernels track near-list membership in a shared-memory table; a duplicate that slips
-        # through a collision is harmless, but a near list may then in theory outgrow its N entries: checked after
-        # every call, never observed; the bitmap variant (8) has no such case
+        # both default kernels track list membership in shared-memory tag tables; a duplicate that slips through a
+        # collision is harmless, but a list may then in theory outgrow its N entries: checked after every call, never
+        # observed; the global-bitmap form of the kernel has no such case
         nc = lib.pb200_sssp_num_ctas(S)
         q2 = empty((nc * 3 * n,), I32)
         b2 = empty((nc * 3 * nwords,), U32)
-        lib.pb200_sssp_set_variant(8)
-        try:
-            with stage("sssp"):
-                call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q2, b2, stats)
-        finally:
-            lib.pb200_sssp_set_variant(12)
+        with stage("sssp"):
+            call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), 1, D, q2, b2, stats)
 
     if SSSP_MODE == "arcrec" and (SSSP_THREADS is not None or S <= 444):
         threads = _sssp_threads(S)
@@ -247,7 +243,7 @@ def sssp_per_source(g: dv.DeviceCSR, sources: torch.Tensor, delta: Optional[floa
     q = empty((n_ctas * 3 * n,), I32)
     bits = empty((n_ctas * 3 * nwords,), U32)
     with stage("sssp"):
-        call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), D, q, bits, stats)
+        call("pb200_sssp_multi", g.indptr, g.indices, g.data, n, sources, S, float(delta), 0, D, q, bits, stats)
     del q, bits
     if int(lib.pb200_sssp_overflowed(_native.stream_ptr())):
         exact_rerun()

@@ -25,207 +25,6 @@
 
 namespace pb200 {
 
-constexpr int SSSP_THREADS = 512;
-constexpr int SSSP_WARPS = SSSP_THREADS / 32;
-
-__global__ void __launch_bounds__(SSSP_THREADS) sssp_flat_kernel(
-    const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ wts, int n,
-    const long long* __restrict__ sources, int n_sources, double delta, double* __restrict__ D,
-    int* __restrict__ q_all, unsigned int* __restrict__ bits_all, long long* __restrict__ stats) {
-  __shared__ int s_cnt[2];
-  __shared__ int s_cnt_far;
-  __shared__ double s_thr;
-  __shared__ double s_red[SSSP_WARPS];
-  __shared__ int s_wtot[SSSP_WARPS];
-  __shared__ int s_wtot2[SSSP_WARPS];
-  __shared__ int s_base_keep, s_base_near;
-  // frontier chunk staged in shared memory
-  __shared__ double c_du[SSSP_THREADS];
-  __shared__ int c_beg[SSSP_THREADS];
-  __shared__ int c_pre[SSSP_THREADS + 1];  // exclusive prefix of degrees
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int* qbuf[2];
-  qbuf[0] = q_all + (size_t)blockIdx.x * 3 * (size_t)n;
-  qbuf[1] = qbuf[0] + n;
-  int* far = qbuf[1] + n;
-  const int nwords = (n + 31) >> 5;
-  // bnear[p]: members of near list p; a vertex clears its bit when it is popped, so the list that
-  // is being filled never needs a separate clearing pass.  bfar: members of the far pile.
-  unsigned int* bnear[2];
-  bnear[0] = bits_all + (size_t)blockIdx.x * 3 * (size_t)nwords;
-  bnear[1] = bnear[0] + nwords;
-  unsigned int* bfar = bnear[1] + nwords;
-
-  for (int s = blockIdx.x; s < n_sources; s += gridDim.x) {
-    double* dist = D + (size_t)s * (size_t)n;
-    const int src = (int)sources[s];
-    for (int i = tid; i < n; i += SSSP_THREADS) dist[i] = INFINITY;
-    for (int i = tid; i < 3 * nwords; i += SSSP_THREADS) bnear[0][i] = 0u;
-    __syncthreads();
-    int p = 0;
-    if (tid == 0) {
-      dist[src] = 0.0;
-      qbuf[0][0] = src;
-      s_cnt[0] = 1; s_cnt[1] = 0; s_cnt_far = 0;
-      s_thr = delta;
-    }
-    __syncthreads();
-    long long rounds = 0, relax = 0, advances = 0;
-
-    for (;;) {
-      // ---------------- near rounds ----------------
-      for (;;) {
-        const int cnt = s_cnt[p];
-        if (cnt == 0) break;
-        ++rounds;
-        const double thr = s_thr;
-        const int* qa = qbuf[p];
-        int* qb = qbuf[p ^ 1];
-        unsigned int* bcur = bnear[p];
-        unsigned int* bnext = bnear[p ^ 1];
-        for (int c0 = 0; c0 < cnt; c0 += SSSP_THREADS) {
-          // (1) one thread per frontier vertex: tentative distance and row extent
-          const int i = c0 + tid;
-          int deg = 0;
-          if (i < cnt) {
-            const int u = qa[i];
-            atomicAnd(&bcur[u >> 5], ~(1u << (u & 31)));   // popped
-            const int b = indptr[u];
-            deg = indptr[u + 1] - b;
-            c_du[tid] = __ldcg(dist + u);
-            c_beg[tid] = b;
-          }
-          // (2) block-wide exclusive scan of the degrees
-          int incl = deg;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-          }
-          if (lane == 31) s_wtot[warp] = incl;
-          __syncthreads();
-          int woff = 0;
-#pragma unroll
-          for (int w = 0; w < SSSP_WARPS; ++w) woff += (w < warp) ? s_wtot[w] : 0;
-          c_pre[tid] = woff + incl - deg;
-          int total = 0;
-#pragma unroll
-          for (int w = 0; w < SSSP_WARPS; ++w) total += s_wtot[w];
-          if (tid == 0) c_pre[SSSP_THREADS] = total;
-          __syncthreads();
-          const int nv = cnt - c0 < SSSP_THREADS ? cnt - c0 : SSSP_THREADS;
-          // (3) one thread per arc (four independent arcs in flight per thread): binary search of
-          // the owning vertex, then the loads of all four chains are issued before any is consumed
-          for (int a0 = tid; a0 < total; a0 += 4 * SSSP_THREADS) {
-            int vv[4];
-            double nd[4], dv[4];
-            bool ok[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int a = a0 + u * SSSP_THREADS;
-              ok[u] = a < total;
-              vv[u] = 0; nd[u] = 0.0;
-              if (ok[u]) {
-                int lo = 0, hi = nv - 1;
-                while (lo < hi) {
-                  const int mid = (lo + hi + 1) >> 1;
-                  if (c_pre[mid] <= a) lo = mid; else hi = mid - 1;
-                }
-                const int e = c_beg[lo] + (a - c_pre[lo]);
-                vv[u] = indices[e];
-                nd[u] = c_du[lo] + wts[e];
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) dv[u] = ok[u] ? __ldcg(dist + vv[u]) : 0.0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (ok[u] && nd[u] < dv[u]) {
-                const int v = vv[u];
-                const double old = atomic_min_pos_f64(dist + v, nd[u]);
-                if (nd[u] < old) {
-                  const unsigned int bit = 1u << (v & 31);
-                  if (nd[u] < thr) {
-                    if (!(atomicOr(&bnext[v >> 5], bit) & bit)) qb[atomicAdd(&s_cnt[p ^ 1], 1)] = v;
-                  } else {
-                    if (!(atomicOr(&bfar[v >> 5], bit) & bit)) far[atomicAdd(&s_cnt_far, 1)] = v;
-                  }
-                }
-              }
-            }
-          }
-          relax += total;  // same value in every thread
-          __syncthreads();
-        }
-        if (tid == 0) s_cnt[p] = 0;  // this buffer is the push target of the round after next
-        p ^= 1;
-        __syncthreads();
-      }
-      // ---------------- advance the threshold ----------------
-      const int nfar = s_cnt_far;
-      if (nfar == 0) break;
-      ++advances;
-      double mn = INFINITY;
-      for (int i = tid; i < nfar; i += SSSP_THREADS) mn = fmin(mn, __ldcg(dist + far[i]));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      if (lane == 0) s_red[warp] = mn;
-      __syncthreads();
-      if (tid == 0) {
-        double m2 = INFINITY;
-        for (int w = 0; w < SSSP_WARPS; ++w) m2 = fmin(m2, s_red[w]);
-        s_thr = m2 + delta;
-        s_base_keep = 0;
-        s_base_near = 0;
-      }
-      __syncthreads();
-      const double thr2 = s_thr;
-      int* qa = qbuf[p];
-      unsigned int* bcur = bnear[p];
-      // split the far pile: entries below the new threshold move to the near list, the rest are
-      // compacted in place (chunks processed in order, so writes trail reads)
-      for (int c0 = 0; c0 < nfar; c0 += SSSP_THREADS) {
-        const int i = c0 + tid;
-        int v = -1;
-        bool to_near = false, keep = false;
-        if (i < nfar) {
-          v = far[i];
-          to_near = __ldcg(dist + v) < thr2;
-          keep = !to_near;
-        }
-        const unsigned mk = __ballot_sync(0xffffffffu, keep);
-        const unsigned mnr = __ballot_sync(0xffffffffu, to_near);
-        if (lane == 0) { s_wtot[warp] = __popc(mk); s_wtot2[warp] = __popc(mnr); }
-        __syncthreads();
-        int offk = 0, offn = 0;
-        for (int w = 0; w < warp; ++w) { offk += s_wtot[w]; offn += s_wtot2[w]; }
-        const int bk = s_base_keep, bn = s_base_near;
-        __syncthreads();  // every thread has read far[i] and the bases
-        if (keep) far[bk + offk + __popc(mk & ((1u << lane) - 1u))] = v;
-        if (to_near) {
-          qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = v;
-          atomicAnd(&bfar[v >> 5], ~(1u << (v & 31)));
-          atomicOr(&bcur[v >> 5], 1u << (v & 31));
-        }
-        if (tid == SSSP_THREADS - 1) {
-          s_base_keep = bk + offk + __popc(mk);
-          s_base_near = bn + offn + __popc(mnr);
-        }
-        __syncthreads();
-      }
-      if (tid == 0) { s_cnt_far = s_base_keep; s_cnt[p] = s_base_near; }
-      __syncthreads();
-    }
-    if (stats && tid == 0) {
-      stats[(size_t)s * 3 + 0] = rounds;
-      stats[(size_t)s * 3 + 1] = relax;
-      stats[(size_t)s * 3 + 2] = advances;
-    }
-    __syncthreads();
-  }
-}
-
-
 // Variant with a GROUP of LPV lanes per frontier vertex (LPV = 8: up to THREADS/8 vertices of a
 // round are expanded at once, each lane issuing the loads of four of its arcs back to back), the
 // popped vertex clearing its own membership bit (no clearing pass) and double-buffered counters
@@ -666,182 +465,16 @@ __global__ void __launch_bounds__(THREADS, 1280 / THREADS) sssp_arcrec_kernel(
 // Variant with one WARP per frontier vertex (lanes = arcs) and a bit-clearing pass per round.
 __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
 
-__global__ void __launch_bounds__(SSSP_THREADS) sssp_warp_kernel(
-    const int* __restrict__ indptr, const int* __restrict__ indices, const double* __restrict__ wts, int n,
-    const long long* __restrict__ sources, int n_sources, double delta, double* __restrict__ D,
-    int* __restrict__ q_all, unsigned int* __restrict__ bits_all, long long* __restrict__ stats) {
-  __shared__ int s_cnt_next, s_cnt_far, s_cnt_near;
-  __shared__ double s_thr;
-  __shared__ double s_red[SSSP_THREADS / 32];
-  __shared__ int s_scan[SSSP_THREADS / 32];
-  __shared__ int s_base_keep, s_base_near;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = SSSP_THREADS / 32;
-  const int nwords = (n + 31) >> 5;
-  int* qa = q_all + (size_t)blockIdx.x * 3 * (size_t)n;
-  int* qb = qa + n;
-  int* far = qb + n;
-  unsigned int* bnear = bits_all + (size_t)blockIdx.x * 3 * (size_t)nwords;
-  unsigned int* bfar = bnear + nwords;
-
-  for (int s = blockIdx.x; s < n_sources; s += gridDim.x) {
-    double* dist = D + (size_t)s * (size_t)n;
-    const int src = (int)sources[s];
-    for (int i = tid; i < n; i += SSSP_THREADS) dist[i] = INFINITY;
-    for (int i = tid; i < nwords; i += SSSP_THREADS) { bnear[i] = 0u; bfar[i] = 0u; }
-    __syncthreads();
-    if (tid == 0) {
-      dist[src] = 0.0;
-      qa[0] = src;
-      s_cnt_near = 1; s_cnt_next = 0; s_cnt_far = 0;
-      s_thr = delta;
-    }
-    __threadfence_block();
-    __syncthreads();
-    long long rounds = 0, relax = 0, advances = 0;
-
-    for (;;) {
-      // ---------------- near rounds ----------------
-      int cnt = s_cnt_near;
-      while (cnt > 0) {
-        // (1) entries of qa leave the "queued" state: clear their bits
-        for (int i = tid; i < cnt; i += SSSP_THREADS) {
-          const int u = qa[i];
-          atomicAnd(&bnear[u >> 5], ~(1u << (u & 31)));
-        }
-        __syncthreads();
-        const double thr = s_thr;
-        // (2) relax the arcs of every queued vertex, one warp per vertex
-        for (int i = warp; i < cnt; i += NW) {
-          const int u = qa[i];
-          const double du = ld_cg_f64(dist + u);
-          const int beg = indptr[u], end = indptr[u + 1];
-          for (int e = beg + lane; e < end; e += 32) {
-            const int v = indices[e];
-            const double nd = du + wts[e];
-            if (nd < ld_cg_f64(dist + v)) {
-              const double old = atomic_min_pos_f64(dist + v, nd);
-              if (nd < old) {
-                const unsigned int bit = 1u << (v & 31);
-                if (nd < thr) {
-                  if (!(atomicOr(&bnear[v >> 5], bit) & bit)) qb[atomicAdd(&s_cnt_next, 1)] = v;
-                } else {
-                  if (!(atomicOr(&bfar[v >> 5], bit) & bit)) far[atomicAdd(&s_cnt_far, 1)] = v;
-                }
-              }
-            }
-          }
-          if (lane == 0) relax += end - beg;
-        }
-        __syncthreads();
-        cnt = s_cnt_next;
-        __syncthreads();
-        if (tid == 0) s_cnt_next = 0;
-        int* t = qa; qa = qb; qb = t;
-        ++rounds;
-        __syncthreads();
-      }
-      // ---------------- advance the threshold ----------------
-      const int nfar = s_cnt_far;
-      if (nfar == 0) break;
-      ++advances;
-      double mn = INFINITY;
-      for (int i = tid; i < nfar; i += SSSP_THREADS) mn = fmin(mn, ld_cg_f64(dist + far[i]));
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-      if (lane == 0) s_red[warp] = mn;
-      __syncthreads();
-      if (tid == 0) {
-        double m2 = INFINITY;
-        for (int q = 0; q < NW; ++q) m2 = fmin(m2, s_red[q]);
-        s_thr = m2 + delta;
-        s_base_keep = 0;
-        s_base_near = 0;
-      }
-      __syncthreads();
-      const double thr2 = s_thr;
-      // split the far pile: entries below the new threshold move to the near list, the
-      // rest are compacted in place (chunks processed in order, so writes trail reads)
-      for (int c0 = 0; c0 < nfar; c0 += SSSP_THREADS) {
-        const int i = c0 + tid;
-        int v = -1;
-        bool to_near = false, keep = false;
-        if (i < nfar) {
-          v = far[i];
-          to_near = ld_cg_f64(dist + v) < thr2;
-          keep = !to_near;
-        }
-        const unsigned mk = __ballot_sync(0xffffffffu, keep);
-        const unsigned mnr = __ballot_sync(0xffffffffu, to_near);
-        if (lane == 0) { s_scan[warp] = __popc(mk); s_red[warp] = (double)__popc(mnr); }
-        __syncthreads();
-        int offk = 0, offn = 0;
-        for (int q = 0; q < warp; ++q) { offk += s_scan[q]; offn += (int)s_red[q]; }
-        const int bk = s_base_keep, bn = s_base_near;
-        __syncthreads();  // every thread has read far[i] and the bases
-        if (keep) far[bk + offk + __popc(mk & ((1u << lane) - 1u))] = v;
-        if (to_near) {
-          qa[bn + offn + __popc(mnr & ((1u << lane) - 1u))] = v;
-          atomicAnd(&bfar[v >> 5], ~(1u << (v & 31)));
-        }
-        if (tid == SSSP_THREADS - 1) {
-          s_base_keep = bk + offk + __popc(mk);
-          s_base_near = bn + offn + __popc(mnr);
-        }
-        __syncthreads();
-      }
-      if (tid == 0) { s_cnt_far = s_base_keep; s_cnt_near = s_base_near; }
-      __syncthreads();
-    }
-    if (stats) {
-      // relax is accumulated per warp leader; reduce over the block
-      double r = (double)relax;
-      r = warp_sum(r);
-      if (lane == 0) s_red[warp] = r;
-      __syncthreads();
-      if (tid == 0) {
-        double tot = 0;
-        for (int q = 0; q < NW; ++q) tot += s_red[q];
-        stats[(size_t)s * 3 + 0] = rounds;
-        stats[(size_t)s * 3 + 1] = (long long)tot;
-        stats[(size_t)s * 3 + 2] = advances;
-      }
-    }
-    __syncthreads();
-  }
-}
-
 }  // namespace pb200
 
 using namespace pb200;
 
 extern "C" {
 
-static int g_sssp_ctas_per_sm = 4;
-// 0: warp per vertex (512 thr), 1: flat thread per arc (512 thr),
-// 2..7: group kernels (threads, lanes per vertex) = (512,8) (256,8) (128,8) (256,32) (128,32) (256,16)
-// 8, 9: (128,8) with five / six arcs in flight per lane
-static int g_sssp_variant = 12;
-static const int kVariantThreads[13] = {512, 512, 512, 256, 128, 256, 128, 256, 128, 128, 128, 128, 128};
-
-int pb200_sssp_set_variant(int v) {
-  if (v < 0 || v > 12) { set_error_msg("pb200_sssp_set_variant: 0..12"); return -1; }
-  g_sssp_variant = v;
-  return 0;
-}
-
-
-// Tuning knob: resident CTAs (= concurrently processed sources) per SM, 1..4.
-int pb200_sssp_set_ctas_per_sm(int c) {
-  if (c < 1 || c > 4) { set_error_msg("pb200_sssp_set_ctas_per_sm: 1..4"); return -1; }
-  g_sssp_ctas_per_sm = c;
-  return 0;
-}
-
-// Number of resident CTAs the launch will use (scratch is sized per CTA).
+// CTAs (= concurrently processed sources) pb200_sssp_multi launches; scratch is sized per CTA.  Up to 9 are
+// resident per SM (128 threads, 56 registers); beyond 16 per SM the CTAs loop over the sources.
 int pb200_sssp_num_ctas(int n_sources) {
-  const int per_sm = (2048 / kVariantThreads[g_sssp_variant]) * g_sssp_ctas_per_sm / 4;
-  const int cap = (per_sm < 1 ? 1 : per_sm) * kSMs;
+  const int cap = 16 * kSMs;
   return n_sources < cap ? n_sources : cap;
 }
 
@@ -850,35 +483,24 @@ int pb200_sssp_num_ctas(int n_sources) {
 // scratch: q[n_ctas * 3 * n] int, bits[n_ctas * 3 * ceil(n/32)] uint32 with
 // n_ctas = pb200_sssp_num_ctas(n_sources); stats (optional) [n_sources][3] int64 =
 // rounds, arcs relaxed, threshold advances.
+// exact_membership = 0: list membership in shared-memory tag tables (the fast kernel; a hash collision can let a
+// duplicate into a list, so a list may in theory outgrow its n entries: pb200_sssp_overflowed tells, never observed);
+// exact_membership != 0: global bitmaps (no such case; the re-run after an overflow).
 int pb200_sssp_multi(const int* indptr, const int* indices, const double* wts, long long n, const long long* sources,
-                     int n_sources, double delta, double* D, int* q, unsigned int* bits, long long* stats,
-                     void* stream) {
+                     int n_sources, double delta, int exact_membership, double* D, int* q, unsigned int* bits,
+                     long long* stats, void* stream) {
   if (n_sources <= 0) return 0;
   if (n >= 1073741823LL) { set_error_msg("pb200_sssp_multi: n too large"); return -1; }
   if (!(delta > 0.0)) { set_error_msg("pb200_sssp_multi: delta must be > 0"); return -1; }
   const int grid = pb200_sssp_num_ctas(n_sources);
-#define PB_SSSP_GROUP(...)                                                                          \
-  sssp_group_kernel<__VA_ARGS__><<<grid, kVariantThreads[g_sssp_variant], 0, (cudaStream_t)stream>>>( \
-      indptr, indices, wts, (int)n, sources, n_sources, delta, D, q, bits, stats)
-  if (g_sssp_variant == 2) PB_SSSP_GROUP(512, 8);
-  else if (g_sssp_variant == 3) PB_SSSP_GROUP(256, 8);
-  else if (g_sssp_variant == 4) PB_SSSP_GROUP(128, 8);
-  else if (g_sssp_variant == 5) PB_SSSP_GROUP(256, 32);
-  else if (g_sssp_variant == 6) PB_SSSP_GROUP(128, 32);
-  else if (g_sssp_variant == 7) PB_SSSP_GROUP(256, 16);
-  else if (g_sssp_variant == 8) PB_SSSP_GROUP(128, 8, 5, 9);    // five arcs per lane: degree <= 40 in one pass, 56 registers
-  else if (g_sssp_variant == 9) PB_SSSP_GROUP(128, 8, 6, 8);
-  else if (g_sssp_variant == 10) PB_SSSP_GROUP(128, 16, 3, 9);
-  else if (g_sssp_variant == 11) PB_SSSP_GROUP(128, 4, 10, 9);
-  else if (g_sssp_variant == 12) PB_SSSP_GROUP(128, 8, 5, 9, true);   // near-list membership in a shared-memory table
-#undef PB_SSSP_GROUP
-  else if (g_sssp_variant == 1)
-    sssp_flat_kernel<<<grid, SSSP_THREADS, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources,
-                                                                    n_sources, delta, D, q, bits, stats);
+  // 128 threads per source, 8 lanes per frontier vertex, five arcs in flight per lane (degree <= 40 in one pass)
+  if (exact_membership)
+    sssp_group_kernel<128, 8, 5, 9, false><<<grid, 128, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources,
+                                                                                   n_sources, delta, D, q, bits, stats);
   else
-    sssp_warp_kernel<<<grid, SSSP_THREADS, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources,
-                                                                    n_sources, delta, D, q, bits, stats);
-  PB_CHECK_LAUNCH("sssp_kernel");
+    sssp_group_kernel<128, 8, 5, 9, true><<<grid, 128, 0, (cudaStream_t)stream>>>(indptr, indices, wts, (int)n, sources,
+                                                                                  n_sources, delta, D, q, bits, stats);
+  PB_CHECK_LAUNCH("sssp_group_kernel");
   return 0;
 }
 
