@@ -172,6 +172,20 @@ int pb200_clip_below(void* a, long long count, double thr, int is_f64, void* str
 int pb200_spmv_long_row(void);
 int pb200_csr_spmv_split_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
                              const int* long_rows, int n_long, const double* x, double* y, void* stream);
+/* rows [row0, row1) of y = A x (y indexed by global row): a rank's slice when the eigensolver is sharded by rows.
+ * long_rows: the rows above pb200_spmv_long_row() entries inside the range */
+int pb200_csr_spmv_rows_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                            long long row0, long long row1, const int* long_rows, int n_long, const double* x,
+                            double* y, void* stream);
+/* SpMV over the nonzero stream: a CTA per pb200_csr_spmv_stream_tile() consecutive nonzeros, rows summed inside the
+ * tile, rows cut by tile boundaries completed from head / tail (n_tiles doubles each; n_tiles = ceil(nnz / tile)).
+ * tile_lo: n_tiles + 1 ints from pb200_csr_spmv_stream_prepare (once per matrix).  Rows [row0, row1) are written;
+ * tiles [tile0, tile1) must cover their nonzeros (tile0 = indptr[row0] / tile, tile1 = ceil(indptr[row1] / tile)) */
+int pb200_csr_spmv_stream_tile(void);
+int pb200_csr_spmv_stream_prepare(const int* indptr, long long n, long long nnz, int* tile_lo, void* stream);
+int pb200_csr_spmv_stream_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                              const int* tile_lo, double* head, double* tail, const double* x, double* y,
+                              long long row0, long long row1, int tile0, int tile1, void* stream);
 int pb200_csr_spmv_window_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
                               const double* x, double* y, void* stream);
 /* relabelled copy: row r' = row perm[r'], columns mapped through inv (inv[perm[i]] = i); indptr_new = prefix sums
@@ -203,6 +217,11 @@ int pb200_lanczos_steps_pro(const int* indptr, const int* indices, const double*
                             int j0, int nsteps, double* alpha, double* beta, double* w, double* h, double* partial,
                             double* tmp, double* om, long long omstride, int* gate, int* counters, double eps,
                             double thresh, void* stream);
+/* step j of pb200_lanczos_steps_pro without its product: w = S v_j (all n entries) is already in place -- the
+ * eigensolver sharded by rows computes its slice with pb200_csr_spmv_rows_f64 and all-gathers w in between */
+int pb200_lanczos_post_pro(long long n, double* V, long long ldv, int j, double* alpha, double* beta, double* w,
+                           double* h, double* partial, double* tmp, double* om, long long omstride, int* gate,
+                           int* counters, double eps, double thresh, void* stream);
 /* Arnoldi steps for a kernel that is not symmetric (utils.py:477-484 takes any kernel): H column-major [ldh][mcap] */
 int pb200_arnoldi_steps(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
                         double* V, long long ldv, int j0, int nsteps, double* H, int ldh, double* w, double* h,

@@ -565,6 +565,12 @@ LANCZOS_WINDOWED = os.environ.get("PB200_LANCZOS_WINDOWED", "1") != "0"
 # pb200_lanczos_steps_pro): ~1 step in 8 instead of every step
 LANCZOS_PRO = os.environ.get("PB200_LANCZOS_PRO", "1") != "0"
 LANCZOS_INITIAL_BASIS = 320       # vectors allocated up front; the basis is re-allocated (doubling) beyond that
+# several ranks: every rank multiplies its slice of the rows, the slices of w are all-gathered, and the (cheap,
+# deterministic) vector part of the step is repeated on every rank -- the basis is never exchanged
+LANCZOS_SHARDED = os.environ.get("PB200_LANCZOS_SHARDED", "1") != "0"
+LANCZOS_SHARD_MIN_ROWS = 65536
+# product over the nonzero stream (one CTA per 1024 nonzeros, no separate kernel for the hub rows)
+SPMV_STREAM = os.environ.get("PB200_SPMV_STREAM", "1") != "0"
 SPMV_WINDOW_KERNEL = os.environ.get("PB200_SPMV_WINDOW", "0") == "1"
 
 
@@ -609,6 +615,32 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
     n_long = int(long_rows.numel())
     if n_long == 0:
         long_rows = None
+    from . import _dist
+    rank, world_size = _dist.world()
+    sharded = bool(LANCZOS_SHARDED and LANCZOS_PRO and world_size > 1 and n >= LANCZOS_SHARD_MIN_ROWS)
+    row0, row1 = 0, n
+    if sharded:
+        import torch.distributed as tdist
+        chunk = round_up(-(-n // world_size), 16)
+        row0, row1 = min(rank * chunk, n), min((rank + 1) * chunk, n)
+    stream_spmv = bool(SPMV_STREAM and LANCZOS_PRO and n >= 32768)
+    if stream_spmv:
+        tile = int(_native.load().pb200_csr_spmv_stream_tile())
+        n_tiles = -(-nnz // tile)
+        tile_lo = empty((n_tiles + 1,), I32)
+        st_head, st_tail = empty((n_tiles,), F64), empty((n_tiles,), F64)
+        call("pb200_csr_spmv_stream_prepare", indptr, n, nnz, tile_lo)
+        if sharded:
+            e0, e1 = (int(v) for v in indptr[torch.tensor([row0, row1], device=indptr.device)].tolist())
+            tile0, tile1 = e0 // tile, -(-e1 // tile)
+        else:
+            tile0, tile1 = 0, n_tiles
+    elif sharded:
+        if long_rows is not None:
+            mine = long_rows[(long_rows >= row0) & (long_rows < row1)].contiguous()
+            long_mine, n_long_mine = (mine, int(mine.numel())) if mine.numel() else (None, 0)
+        else:
+            long_mine, n_long_mine = None, 0
     ld = n
     nblk = n // 2048 + 1
     # the basis grows on demand (the cap is ~2000 vectors = 16 GB at 1 M cells; 200 are used there)
@@ -617,7 +649,7 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
     V32 = empty((cap + 1, ld), F32) if (LANCZOS_FP32_SHADOW and not LANCZOS_PRO) else None
     alpha = zeros((max_basis + 1,), F64)
     beta = zeros((max_basis + 2,), F64)
-    w = empty((n,), F64)
+    w = empty((world_size * chunk,), F64) if sharded else empty((n,), F64)
     h = empty((max_basis + 1,), F64)
     partial = empty(((max_basis + 1) * nblk,), F64)
     tmp = empty((1,), F64)
@@ -645,7 +677,20 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
                 V32 = V32_new
             del V_new
         with stage("lanczos_steps"):
-            if LANCZOS_PRO:
+            if sharded or stream_spmv:
+                w_mine = w[rank * chunk:(rank + 1) * chunk] if sharded else None
+                for j in range(m, m + steps):
+                    if stream_spmv:
+                        call("pb200_csr_spmv_stream_f64", indptr, indices, svals, n, nnz, tile_lo, st_head, st_tail,
+                             V[j], w, row0, row1, tile0, tile1)
+                    else:
+                        call("pb200_csr_spmv_rows_f64", indptr, indices, svals, n, nnz, row0, row1, long_mine,
+                             n_long_mine, V[j], w)
+                    if sharded:
+                        tdist.all_gather_into_tensor(w, w_mine)
+                    call("pb200_lanczos_post_pro", n, V, ld, j, alpha, beta, w, h, partial, tmp, om, omstride, gate,
+                         counters, eps_eff, 1.5e-8)
+            elif LANCZOS_PRO:
                 call("pb200_lanczos_steps_pro", indptr, indices, svals, n, nnz, long_rows, n_long, V, ld, V32,
                      int(perm is not None and SPMV_WINDOW_KERNEL), m, steps,
                      alpha, beta, w, h, partial, tmp, om, omstride, gate, counters, eps_eff, 1.5e-8)
@@ -669,10 +714,19 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
         if resid.max() < 1e-3 * max(1e-3, np.abs(theta).max()):
             step_batch = max(1, min(batch, 5))
         exhausted = (m >= n) or (b[m - 1] <= 1e-14 * max(1.0, np.abs(theta_all).max()))
-        if np.all(resid <= tol * np.maximum(np.abs(theta), 1e-3)) or exhausted:
+        done = bool(np.all(resid <= tol * np.maximum(np.abs(theta), 1e-3)) or exhausted)
+        if sharded:
+            # the ranks run identical kernels on identical data, so they agree; rank 0's word is taken anyway,
+            # because a disagreement would leave the all-gathers of the next batch unmatched
+            ctl = torch.tensor([int(done), step_batch], dtype=torch.int64, device=V.device)
+            _dist.broadcast_(ctl)
+            done, step_batch = bool(ctl[0].item()), int(ctl[1].item())
+        if done:
             info["converged"] = True
             break
     info["reorthogonalised_steps"] = int(counters.item()) if LANCZOS_PRO else m
+    info["row_sharded_over"] = world_size if sharded else 1
+    info["spmv"] = "nonzero stream" if stream_spmv else "row kernels"
     if not info["converged"]:
         raise RuntimeError(
             f"Lanczos did not converge in {m} steps (max residual {info.get('max_resid')}); "

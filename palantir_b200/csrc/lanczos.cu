@@ -27,15 +27,16 @@ namespace pb200 {
 // ---------------------------------------------------------------------------
 constexpr int SPMV_LONG_ROW = 128;   // rows above this many entries go to csr_spmv_long_rows_kernel when a list is given
 
+// Rows [row0, row1) of the product (the whole matrix by default; a rank's slice when the eigensolver is row-sharded).
 template <int L>
 __global__ void __launch_bounds__(256) csr_spmv_kernel(const int* __restrict__ indptr,
                                                        const int* __restrict__ indices,
                                                        const double* __restrict__ vals,
                                                        const double* __restrict__ x, double* __restrict__ y,
-                                                       long long n, int skip_long) {
+                                                       long long row0, long long row1, int skip_long) {
   const int lane = threadIdx.x & (L - 1);
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
-  if (row >= n) return;  // whole sub-warp leaves together
+  const long long row = row0 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) / L;
+  if (row >= row1) return;  // whole sub-warp leaves together
   const int beg = indptr[row], end = indptr[row + 1];
   if (skip_long && end - beg > SPMV_LONG_ROW) return;
   double s0 = 0.0, s1 = 0.0;
@@ -53,6 +54,110 @@ __global__ void __launch_bounds__(256) csr_spmv_kernel(const int* __restrict__ i
   if (lane == 0) y[row] = s;
 }
 
+// ---------------------------------------------------------------------------
+// SpMV over the NONZERO stream ("CSR-stream"): a CTA takes ST_TILE consecutive nonzeros whatever rows they belong to,
+// so the hubs of the symmetrised kNN graph (rows of up to ~4000 entries at 1 M cells, 13 % of the nonzeros in 5 % of
+// the rows) cost what their nonzeros cost and need no kernel of their own.  Phase 1: every thread loads four
+// (column, value) pairs -- coalesced, aligned to the tile, not to row starts -- and issues its four x gathers
+// back to back; the products go to shared memory.  Phase 2: groups of 16 lanes sum the row segments of the tile
+// (lane-strided partial sums, then a shuffle tree: the order is fixed, results are reproducible).  A row that lies
+// inside one tile is written to y; a row cut by a tile boundary leaves its pieces in tail[tile] (the piece that
+// starts the row) and head[tile] (the pieces that continue it), which csr_stream_fixup_kernel adds in tile order.
+// tile_lo[b] = first row that STARTS at or after nonzero b * ST_TILE (csr_stream_tiles_kernel, once per matrix).
+// ---------------------------------------------------------------------------
+constexpr int ST_TILE = 1024;     // nonzeros per CTA (4 per thread)
+constexpr int ST_THREADS = 256;
+
+__global__ void csr_stream_tiles_kernel(const int* __restrict__ indptr, long long n, long long nnz, int n_tiles,
+                                        int* __restrict__ tile_lo) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > n_tiles) return;
+  if (b == n_tiles) { tile_lo[b] = (int)n; return; }
+  const long long target = (long long)b * ST_TILE;
+  // first r in [0, n] with indptr[r] >= target
+  long long lo = 0, hi = n;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if ((long long)indptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  tile_lo[b] = (int)lo;
+}
+
+__global__ void __launch_bounds__(ST_THREADS) csr_spmv_stream_kernel(const int* __restrict__ indptr,
+                                                                     const int* __restrict__ indices,
+                                                                     const double* __restrict__ vals,
+                                                                     const double* __restrict__ x, double* __restrict__ y,
+                                                                     long long nnz, const int* __restrict__ tile_lo,
+                                                                     double* __restrict__ head, double* __restrict__ tail,
+                                                                     int tile0, long long row0, long long row1) {
+  __shared__ double prod[ST_TILE];
+  const int b = tile0 + blockIdx.x;
+  const long long base = (long long)b * ST_TILE;
+  long long end = base + ST_TILE;
+  if (end > nnz) end = nnz;
+  const int lo = tile_lo[b], hi = tile_lo[b + 1];          // rows starting in this tile: [lo, hi)
+  {
+    int c[4];
+    double v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const long long e = base + threadIdx.x + t * ST_THREADS;
+      const bool ok = e < end;
+      c[t] = ok ? __ldg(indices + e) : 0;
+      v[t] = ok ? __ldg(vals + e) : 0.0;
+    }
+    double xg[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) xg[t] = __ldg(x + c[t]);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) prod[threadIdx.x + t * ST_THREADS] = v[t] * xg[t];
+  }
+  // the nonzero at `base` belongs to a row that started in an earlier tile unless row `lo` starts exactly there
+  // (tile_lo = first row with indptr >= base, so indptr[lo - 1] < base whenever indptr[lo] > base)
+  const int has_prev = (long long)indptr[lo] > base ? 1 : 0;
+  const int nseg = has_prev + (hi - lo);
+  const int lane = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  const unsigned half_mask = 0xffffu << (threadIdx.x & 16);   // the 16 lanes of this group (groups of a warp may differ in trip count)
+  __syncthreads();
+  for (int sgm = grp; sgm < nseg; sgm += ST_THREADS / 16) {
+    const bool prev = has_prev && sgm == 0;
+    const long long r = prev ? lo - 1 : lo + sgm - has_prev;
+    const long long rb = prev ? base : (long long)indptr[r];
+    const long long re_full = (long long)indptr[r + 1];
+    const long long re = re_full < end ? re_full : end;
+    double sum = 0.0;
+    for (long long e = rb + lane; e < re; e += 16) sum += prod[e - base];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(half_mask, sum, o, 16);
+    if (lane == 0) {
+      if (prev) head[b] = sum;
+      else if (re_full > end) tail[b] = sum;
+      else if (r >= row0 && r < row1) y[r] = sum;
+    }
+  }
+}
+
+// rows cut by tile boundaries: y[r] = tail[first tile] + head[next tiles...] in tile order.  One thread per tile.
+__global__ void csr_stream_fixup_kernel(const int* __restrict__ indptr, long long nnz, const int* __restrict__ tile_lo,
+                                        const double* __restrict__ head, const double* __restrict__ tail,
+                                        double* __restrict__ y, int tile0, int tile1, long long row0, long long row1) {
+  const int b = tile0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= tile1) return;
+  const int lo = tile_lo[b], hi = tile_lo[b + 1];
+  if (hi <= lo) return;
+  const long long r = hi - 1;                                // last row starting in this tile
+  const long long re = (long long)indptr[r + 1];
+  long long end = (long long)(b + 1) * ST_TILE;
+  if (re <= end) return;                                     // it also ends here
+  if (r < row0 || r >= row1) return;
+  double acc = tail[b];
+  for (int c = b + 1;; ++c) {
+    acc += head[c];
+    end += ST_TILE;
+    if (re <= end) break;
+  }
+  y[r] = acc;
+}
 
 // ---------------------------------------------------------------------------
 // SpMV with the x window staged in shared memory, for matrices whose rows are in a
@@ -355,6 +460,20 @@ __global__ void clip_below_kernel(TX* __restrict__ a, long long count, TX thr) {
 constexpr int VB = 256;        // threads
 constexpr int VCHUNK = 2048;   // elements per block (8 per thread)
 
+// sum of partial[0..nblk) with the summation order of reduce_partials_kernel at 256 threads; all threads get it
+__device__ __forceinline__ double block_sum_partials(const double* partial, int nblk, double* red) {
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += VB) s += partial[b];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll
+  for (int q = 0; q < VB / 32; ++q) tot += red[q];
+  __syncthreads();
+  return tot;
+}
+
 // partial[c * nblk + b] = sum_{i in chunk b} V[c][i] * w[i],  c = 0..m-1
 template <typename TV>
 __global__ void __launch_bounds__(VB) multi_dot_kernel(const TV* __restrict__ V, long long ldv, int m,
@@ -391,9 +510,11 @@ __global__ void __launch_bounds__(VB) multi_dot_kernel(const TV* __restrict__ V,
 }
 
 // h[c] = sum_b partial[c][b]; optionally hacc[c] += h[c]
+// fix_j >= 0: additionally alpha_fix[fix_j] += h[fix_j] (the Gram-Schmidt pass's correction of alpha_j)
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, int nblk, int m,
                                        double* __restrict__ h, double* __restrict__ hacc,
-                                       const int* __restrict__ gate = nullptr) {
+                                       const int* __restrict__ gate = nullptr, int fix_j = -1,
+                                       double* __restrict__ alpha_fix = nullptr) {
   const int c = blockIdx.x;
   if (c >= m) return;
   if (gate && *gate == 0) return;
@@ -408,6 +529,7 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, int n
     for (int q = 0; q < (int)(blockDim.x >> 5); ++q) tot += red[q];
     h[c] = tot;
     if (hacc) hacc[c] += tot;
+    if (c == fix_j) alpha_fix[c] += tot;
   }
 }
 
@@ -468,11 +590,21 @@ __global__ void recurrence_coeffs_kernel(const double* __restrict__ alpha, const
 // estimates for v_{j+1}, and raises gate[0] when one of them exceeds `thresh` (or when the previous step did:
 // the reorthogonalisation is always done on two consecutive vectors, gate[1] carries the second).  A raised gate
 // makes the gated Gram-Schmidt kernels that follow do their work; the estimates are then reset to eps.
+// nrm2_partials != NULL (blockDim.x == 256): |w|^2 = their sum (as reduce_partials_kernel<<<1, 256>>> forms it),
+// also stored to *nrm2 for the kernels that follow.
 __global__ void lanczos_omega_kernel(const double* __restrict__ alpha, const double* __restrict__ beta, int j,
-                                     const double* __restrict__ nrm2, double* __restrict__ om, long long omstride,
-                                     double eps, double thresh, int* __restrict__ gate, int* __restrict__ counters) {
+                                     double* nrm2, double* __restrict__ om, long long omstride,
+                                     double eps, double thresh, int* __restrict__ gate, int* __restrict__ counters,
+                                     const double* nrm2_partials = nullptr, int nblk = 0) {
   __shared__ double red[8];
-  const double bj1 = sqrt(*nrm2);
+  double n2;
+  if (nrm2_partials) {
+    n2 = block_sum_partials(nrm2_partials, nblk, red);
+    if (threadIdx.x == 0) *nrm2 = n2;
+  } else {
+    n2 = *nrm2;
+  }
+  const double bj1 = sqrt(n2);
   const double* cur = om + (long long)(j % 3) * omstride;            // omega_{j, .}
   const double* prv = om + (long long)((j + 2) % 3) * omstride;      // omega_{j-1, .}
   double* nxt = om + (long long)((j + 1) % 3) * omstride;            // omega_{j+1, .}
@@ -516,6 +648,106 @@ __global__ void lanczos_omega_kernel(const double* __restrict__ alpha, const dou
 __global__ void lanczos_fix_alpha_kernel(const double* __restrict__ h, int j, double* __restrict__ alpha,
                                          const int* __restrict__ gate) {
   if (threadIdx.x == 0 && *gate) alpha[j] += h[j];
+}
+
+// ---------------------------------------------------------------------------
+// Fused forms of the per-step vector kernels (pb200_lanczos_post_pro): the same arithmetic in the same order as the
+// separate kernels above -- every block re-derives a scalar from the per-block partial sums exactly as
+// reduce_partials_kernel<<<1, 256>>> does -- so that a step is 7 launches after the SpMV instead of 14.
+// ---------------------------------------------------------------------------
+// alpha_j = sum of pa[] (the partial sums of v_j . w);  w -= beta_j v_{j-1} + alpha_j v_j;  pb[block] = partial |w|^2
+__global__ void __launch_bounds__(VB) lanczos_recur_kernel(const double* __restrict__ vj, const double* __restrict__ vjm1,
+                                                           const double* pa, int nblk, double* alpha,
+                                                           const double* __restrict__ beta, int j, double* w,
+                                                           long long n, double* pb) {
+  __shared__ double red[VB / 32];
+  const double a = block_sum_partials(pa, nblk, red);
+  const double bj = j > 0 ? beta[j] : 0.0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) alpha[j] = a;
+  const long long base = (long long)blockIdx.x * VCHUNK;
+  double s = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const long long i = base + threadIdx.x + (long long)t * VB;
+    if (i < n) {
+      double acc = 0.0;
+      if (vjm1) acc = fma(bj, vjm1[i], acc);
+      acc = fma(a, vj[i], acc);
+      const double wn = w[i] - acc;
+      w[i] = wn;
+      s = fma(wn, wn, s);
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < VB / 32; ++q) tot += red[q];
+    pb[blockIdx.x] = tot;
+  }
+}
+
+// gated: w -= sum_c h[c] V[c], then pb[block] = partial |w|^2 of the result
+__global__ void __launch_bounds__(VB) multi_axpy_nrm2_kernel(const double* __restrict__ V, long long ldv, int m,
+                                                             const double* __restrict__ h, double* w, long long n,
+                                                             double* pb, const int* __restrict__ gate) {
+  extern __shared__ double hs[];
+  __shared__ double red[VB / 32];
+  if (*gate == 0) return;
+  for (int c = threadIdx.x; c < m; c += VB) hs[c] = h[c];
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * VCHUNK;
+  double acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.0;
+  for (int c = 0; c < m; ++c) {
+    const double* v = V + (long long)c * ldv;
+    const double hc = hs[c];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const long long i = base + threadIdx.x + (long long)t * VB;
+      if (i < n) acc[t] = fma(hc, v[i], acc[t]);
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const long long i = base + threadIdx.x + (long long)t * VB;
+    if (i < n) {
+      const double wn = w[i] - acc[t];
+      w[i] = wn;
+      s = fma(wn, wn, s);
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < VB / 32; ++q) tot += red[q];
+    pb[blockIdx.x] = tot;
+  }
+}
+
+// v_{j+1} = w / beta_{j+1}, beta_{j+1} = sqrt(|w|^2): |w|^2 from tmp (the omega kernel's) or, when the gate is up (w was
+// re-orthogonalised), from the partial sums pb[] of multi_axpy_nrm2_kernel
+__global__ void __launch_bounds__(VB) lanczos_scale_kernel(const double* __restrict__ w, double* tmp, const double* pb,
+                                                           int nblk, const int* __restrict__ gate,
+                                                           double* __restrict__ out, long long n, double* beta_out) {
+  __shared__ double red[VB / 32];
+  double nrm2;
+  if (*gate) {
+    nrm2 = block_sum_partials(pb, nblk, red);
+  } else {
+    nrm2 = *tmp;
+  }
+  const double b = sqrt(nrm2);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *beta_out = b;
+  if (i < n) out[i] = b > 0.0 ? w[i] / b : 0.0;
 }
 
 // Arnoldi bookkeeping: H[0..j][j] = h + h2 (two Gram-Schmidt passes), H[j+1][j] = sqrt(nrm2); H column-major, ldh rows
@@ -611,12 +843,14 @@ static int launch_spmv_window(const int* indptr, const int* indices, const doubl
   return 0;
 }
 
-static int launch_spmv(const int* indptr, const int* indices, const double* vals, const double* x, double* y,
-                       long long n, long long nnz, cudaStream_t st, int windowed = 0, const int* long_rows = nullptr,
-                       int n_long = 0) {
-  if (windowed && n >= 4 * SW_C) return launch_spmv_window(indptr, indices, vals, x, y, n, st);
+// y[row0..row1) = (A x)[row0..row1).  long_rows (optional): the rows above SPMV_LONG_ROW entries INSIDE that range.
+static int launch_spmv_rows(const int* indptr, const int* indices, const double* vals, const double* x, double* y,
+                            long long n, long long nnz, long long row0, long long row1, cudaStream_t st,
+                            const int* long_rows, int n_long) {
   const double mean = n > 0 ? (double)nnz / (double)n : 0.0;
   const int skip = (long_rows != nullptr && n_long > 0) ? 1 : 0;
+  const long long nr = row1 - row0;
+  if (nr <= 0) return 0;
   if (skip) {
     // the long rows first: they are the longest-running warps
     csr_spmv_long_rows_kernel<<<div_up((long long)n_long * 32, 256), 256, 0, st>>>(indptr, indices, vals, x, y, long_rows,
@@ -624,14 +858,21 @@ static int launch_spmv(const int* indptr, const int* indices, const double* vals
     PB_CHECK_LAUNCH("csr_spmv_long_rows_kernel");
   }
   if (mean > 24.0) {
-    csr_spmv_kernel<16><<<div_up(n * 16, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n, skip);
+    csr_spmv_kernel<16><<<div_up(nr * 16, 256), 256, 0, st>>>(indptr, indices, vals, x, y, row0, row1, skip);
   } else if (mean > 12.0) {
-    csr_spmv_kernel<8><<<div_up(n * 8, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n, skip);
+    csr_spmv_kernel<8><<<div_up(nr * 8, 256), 256, 0, st>>>(indptr, indices, vals, x, y, row0, row1, skip);
   } else {
-    csr_spmv_kernel<4><<<div_up(n * 4, 256), 256, 0, st>>>(indptr, indices, vals, x, y, n, skip);
+    csr_spmv_kernel<4><<<div_up(nr * 4, 256), 256, 0, st>>>(indptr, indices, vals, x, y, row0, row1, skip);
   }
   PB_CHECK_LAUNCH("csr_spmv_kernel");
   return 0;
+}
+
+static int launch_spmv(const int* indptr, const int* indices, const double* vals, const double* x, double* y,
+                       long long n, long long nnz, cudaStream_t st, int windowed = 0, const int* long_rows = nullptr,
+                       int n_long = 0) {
+  if (windowed && n >= 4 * SW_C) return launch_spmv_window(indptr, indices, vals, x, y, n, st);
+  return launch_spmv_rows(indptr, indices, vals, x, y, n, nnz, 0, n, st, long_rows, n_long);
 }
 
 static int nrm2_into(const double* w, long long n, double* partial, double* out, cudaStream_t st) {
@@ -673,6 +914,54 @@ int pb200_spmv_long_row(void) { return SPMV_LONG_ROW; }
 int pb200_csr_spmv_split_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
                              const int* long_rows, int n_long, const double* x, double* y, void* stream) {
   return launch_spmv(indptr, indices, vals, x, y, n, nnz, (cudaStream_t)stream, 0, long_rows, n_long);
+}
+
+// Rows [row0, row1) of y = A x (a rank's slice when the eigensolver is sharded by rows; y is indexed by the global
+// row).  long_rows: the rows above pb200_spmv_long_row() entries inside the range.
+int pb200_csr_spmv_rows_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                            long long row0, long long row1, const int* long_rows, int n_long, const double* x,
+                            double* y, void* stream) {
+  if (row0 < 0 || row1 > n || row0 > row1) { set_error_msg("pb200_csr_spmv_rows_f64: need 0 <= row0 <= row1 <= n"); return -1; }
+  return launch_spmv_rows(indptr, indices, vals, x, y, n, nnz, row0, row1, (cudaStream_t)stream, long_rows, n_long);
+}
+
+// CSR-stream SpMV (csr_spmv_stream_kernel): nonzeros per tile; tiles of a matrix = ceil(nnz / tile).
+int pb200_csr_spmv_stream_tile(void) { return ST_TILE; }
+
+// tile_lo[0 .. n_tiles] for pb200_csr_spmv_stream_f64 (once per matrix; n_tiles = ceil(nnz / tile), n_tiles + 1 ints).
+int pb200_csr_spmv_stream_prepare(const int* indptr, long long n, long long nnz, int* tile_lo, void* stream) {
+  const int n_tiles = (int)div_up(nnz, ST_TILE);
+  csr_stream_tiles_kernel<<<div_up(n_tiles + 1, 256), 256, 0, (cudaStream_t)stream>>>(indptr, n, nnz, n_tiles, tile_lo);
+  PB_CHECK_LAUNCH("csr_stream_tiles_kernel");
+  return 0;
+}
+
+static int launch_spmv_stream(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                              const int* tile_lo, double* head, double* tail, const double* x, double* y,
+                              long long row0, long long row1, int tile0, int tile1, cudaStream_t st) {
+  if (tile1 <= tile0) return 0;
+  csr_spmv_stream_kernel<<<tile1 - tile0, ST_THREADS, 0, st>>>(indptr, indices, vals, x, y, nnz, tile_lo, head, tail,
+                                                              tile0, row0, row1);
+  PB_CHECK_LAUNCH("csr_spmv_stream_kernel");
+  csr_stream_fixup_kernel<<<div_up(tile1 - tile0, 256), 256, 0, st>>>(indptr, nnz, tile_lo, head, tail, y, tile0, tile1,
+                                                                     row0, row1);
+  PB_CHECK_LAUNCH("csr_stream_fixup_kernel");
+  return 0;
+}
+
+// y[row0..row1) = (A x)[row0..row1) over the nonzero stream: tiles [tile0, tile1) must cover the nonzeros of those rows
+// (tile0 = indptr[row0] / tile, tile1 = ceil(indptr[row1] / tile); the whole matrix: rows [0, n), tiles [0, n_tiles)).
+// head / tail: n_tiles doubles of scratch each.  Rows without entries are not written (zero y first if there are any).
+int pb200_csr_spmv_stream_f64(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
+                              const int* tile_lo, double* head, double* tail, const double* x, double* y,
+                              long long row0, long long row1, int tile0, int tile1, void* stream) {
+  const int n_tiles = (int)div_up(nnz, ST_TILE);
+  if (row0 < 0 || row1 > n || row0 > row1 || tile0 < 0 || tile1 > n_tiles) {
+    set_error_msg("pb200_csr_spmv_stream_f64: bad row or tile range");
+    return -1;
+  }
+  return launch_spmv_stream(indptr, indices, vals, n, nnz, tile_lo, head, tail, x, y, row0, row1, tile0, tile1,
+                            (cudaStream_t)stream);
 }
 
 int pb200_csr_spmm_f32(const int* indptr, const int* indices, const double* vals, long long n, const float* x,
@@ -791,58 +1080,69 @@ int pb200_lanczos_steps(const int* indptr, const int* indices, const double* val
   return 0;
 }
 
+// Everything of Lanczos step j that follows the product w = S v_j, with partial reorthogonalisation (see
+// pb200_lanczos_steps_pro): alpha_j, the three-term recurrence, |w|^2, the omega recurrence and its gate, the gated
+// Gram-Schmidt pass over V[0..j], v_{j+1} and beta_{j+1}.  Seven launches (fused kernels, same arithmetic as the
+// separate ones of pb200_lanczos_steps).
+static int lanczos_post_pro(long long n, double* V, long long ldv, int j, double* alpha, double* beta, double* w,
+                            double* h, double* partial, double* tmp, double* om, long long omstride, int* gate,
+                            int* counters, double eps, double thresh, cudaStream_t st) {
+  const int nblk = div_up(n, VCHUNK);
+  const int m = j + 1;
+  double* pa = partial;             // partial sums of v_j . w
+  double* pb = partial + nblk;      // partial sums of |w|^2 (needs partial[>= 2 nblk]: mcap >= 2)
+  const double* vj = V + (long long)j * ldv;
+  multi_dot_kernel<double><<<nblk, VB, 0, st>>>(vj, ldv, 1, w, n, pa);
+  PB_CHECK_LAUNCH("multi_dot_kernel(alpha)");
+  lanczos_recur_kernel<<<nblk, VB, 0, st>>>(vj, j > 0 ? vj - ldv : nullptr, pa, nblk, alpha, beta, j, w, n, pb);
+  PB_CHECK_LAUNCH("lanczos_recur_kernel");
+  lanczos_omega_kernel<<<1, 256, 0, st>>>(alpha, beta, j, tmp, om, omstride, eps, thresh, gate, counters, pb, nblk);
+  PB_CHECK_LAUNCH("lanczos_omega_kernel");
+  // gated: one Gram-Schmidt pass against V[0..j], alpha correction, new norm.  The FP64 basis, not an FP32
+  // shadow: here the pass has to bring the overlaps down from ~1e-8 to round-off (the estimates are reset to
+  // eps afterwards), and a shadow vector's 6e-8 rounding error, dotted with a w of norm beta, puts ~1e-9 back
+  multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V, ldv, m, w, n, partial, gate);
+  PB_CHECK_LAUNCH("multi_dot_kernel(gated)");
+  reduce_partials_kernel<<<m, 256, 0, st>>>(partial, nblk, m, h, nullptr, gate, j, alpha);
+  PB_CHECK_LAUNCH("reduce_partials_kernel(gated)");
+  multi_axpy_nrm2_kernel<<<nblk, VB, sizeof(double) * m, st>>>(V, ldv, m, h, w, n, pb, gate);
+  PB_CHECK_LAUNCH("multi_axpy_nrm2_kernel(gated)");
+  lanczos_scale_kernel<<<div_up(n, VB), VB, 0, st>>>(w, tmp, pb, nblk, gate, V + (long long)(j + 1) * ldv, n,
+                                                    beta + j + 1);
+  PB_CHECK_LAUNCH("lanczos_scale_kernel");
+  return 0;
+}
+
 // The same recurrence with PARTIAL reorthogonalisation: the Gram-Schmidt pass over the whole basis runs only when
 // the omega recurrence (lanczos_omega_kernel) says that orthogonality is about to drop below `thresh`
 // (~sqrt(machine eps)), on two consecutive steps each time; in between only the three-term recurrence runs.
 // Semi-orthogonality at that level keeps the Ritz values accurate to round-off and the Ritz vectors to ~1e-8
 // (Simon 1984).  om: 3 * (mcap + 2) doubles, om[0] = 1 before the first step; gate: 2 ints, zero before the first step;
-// counters[0] counts the reorthogonalised steps.  Everything else as pb200_lanczos_steps.
+// counters[0] counts the reorthogonalised steps.  V32 is not used (kept for the ABI).  Everything else as
+// pb200_lanczos_steps.
 int pb200_lanczos_steps_pro(const int* indptr, const int* indices, const double* vals, long long n, long long nnz,
                             const int* long_rows, int n_long, double* V, long long ldv, float* V32, int windowed,
                             int j0, int nsteps, double* alpha, double* beta, double* w, double* h, double* partial,
                             double* tmp, double* om, long long omstride, int* gate, int* counters, double eps,
                             double thresh, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  const int nblk = div_up(n, VCHUNK);
+  (void)V32;
   for (int j = j0; j < j0 + nsteps; ++j) {
-    const int m = j + 1;
     int rc = launch_spmv(indptr, indices, vals, V + (long long)j * ldv, w, n, nnz, st, windowed, long_rows, n_long);
     if (rc) return rc;
-    multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V + (long long)j * ldv, ldv, 1, w, n, partial);
-    PB_CHECK_LAUNCH("multi_dot_kernel(alpha)");
-    reduce_partials_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, alpha + j, nullptr);
-    PB_CHECK_LAUNCH("reduce_partials_kernel(alpha)");
-    recurrence_coeffs_kernel<<<1, 32, 0, st>>>(alpha, beta, j, h);
-    PB_CHECK_LAUNCH("recurrence_coeffs_kernel");
-    if (j > 0)
-      multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * 2, st>>>(V + (long long)(j - 1) * ldv, ldv, 2, h, w, n);
-    else
-      multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * 1, st>>>(V, ldv, 1, h + 1, w, n);
-    PB_CHECK_LAUNCH("multi_axpy_kernel(recurrence)");
-    rc = nrm2_into(w, n, partial, tmp, st);
+    rc = lanczos_post_pro(n, V, ldv, j, alpha, beta, w, h, partial, tmp, om, omstride, gate, counters, eps, thresh, st);
     if (rc) return rc;
-    lanczos_omega_kernel<<<1, 256, 0, st>>>(alpha, beta, j, tmp, om, omstride, eps, thresh, gate, counters);
-    PB_CHECK_LAUNCH("lanczos_omega_kernel");
-    // gated: one Gram-Schmidt pass against V[0..j], alpha correction, new norm.  The FP64 basis, not its FP32
-    // shadow: here the pass has to bring the overlaps down from ~1e-8 to round-off (the estimates are reset to
-    // eps afterwards), and a shadow vector's 6e-8 rounding error, dotted with a w of norm beta, puts ~1e-9 back
-    multi_dot_kernel<double><<<nblk, VB, 0, st>>>(V, ldv, m, w, n, partial, gate);
-    PB_CHECK_LAUNCH("multi_dot_kernel(gated)");
-    reduce_partials_kernel<<<m, 256, 0, st>>>(partial, nblk, m, h, nullptr, gate);
-    PB_CHECK_LAUNCH("reduce_partials_kernel(gated)");
-    lanczos_fix_alpha_kernel<<<1, 32, 0, st>>>(h, j, alpha, gate);
-    PB_CHECK_LAUNCH("lanczos_fix_alpha_kernel");
-    multi_axpy_kernel<double><<<nblk, VB, sizeof(double) * m, st>>>(V, ldv, m, h, w, n, gate);
-    PB_CHECK_LAUNCH("multi_axpy_kernel(gated)");
-    multi_dot_kernel<double><<<nblk, VB, 0, st>>>(w, 0, 1, w, n, partial, gate);
-    PB_CHECK_LAUNCH("multi_dot_kernel(nrm2, gated)");
-    reduce_partials_kernel<<<1, 256, 0, st>>>(partial, nblk, 1, tmp, nullptr, gate);
-    PB_CHECK_LAUNCH("reduce_partials_kernel(nrm2, gated)");
-    scale_by_norm_kernel<<<div_up(n, 256), 256, 0, st>>>(w, tmp, V + (long long)(j + 1) * ldv,
-                                                         V32 ? V32 + (long long)(j + 1) * ldv : nullptr, n, beta + j + 1);
-    PB_CHECK_LAUNCH("scale_by_norm_kernel");
   }
   return 0;
+}
+
+// Step j of pb200_lanczos_steps_pro WITHOUT its product: the caller has put w = S v_j (all n entries) in place --
+// the eigensolver sharded by rows computes its slice with pb200_csr_spmv_rows_f64 and all-gathers w in between.
+int pb200_lanczos_post_pro(long long n, double* V, long long ldv, int j, double* alpha, double* beta, double* w,
+                           double* h, double* partial, double* tmp, double* om, long long omstride, int* gate,
+                           int* counters, double eps, double thresh, void* stream) {
+  return lanczos_post_pro(n, V, ldv, j, alpha, beta, w, h, partial, tmp, om, omstride, gate, counters, eps, thresh,
+                          (cudaStream_t)stream);
 }
 
 // Arnoldi steps j = j0 .. j0+nsteps-1 for a general (non-symmetric) CSR matrix, e.g. T = D^-1 K of a kernel that

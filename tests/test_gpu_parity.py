@@ -639,6 +639,114 @@ def test_spmv_with_hub_rows_vs_scipy(pb):
     assert np.max(np.abs(y.cpu().numpy() - ref)) < 1e-12 * max(1.0, np.abs(ref).max())
 
 
+def test_spmv_row_ranges_and_nonzero_stream_vs_scipy(pb):
+    """The products the eigensolver is built from -- a rank's row range, the kernel over the nonzero stream (rows cut
+    by tile boundaries, hubs spanning several tiles, empty rows) -- against scipy."""
+    import torch
+    from scipy.sparse import random as sprandom
+    from palantir_b200 import _device as dv, _native
+
+    rng = np.random.default_rng(5)
+    n = 30_000
+    a = sprandom(n, n, density=50 / n, random_state=5, format="lil")
+    for r, ln in ((0, 3000), (5, 129), (77, 1024), (78, 1), (n - 1, 5000), (1234, 2048), (20_000, 0), (20_001, 0)):
+        cols = rng.choice(n, ln, replace=False)
+        a.rows[r] = sorted(cols.tolist()); a.data[r] = rng.normal(size=ln).tolist()
+    a = a.tocsr()
+    x = rng.normal(size=n)
+    ref = a @ x
+    scale = max(1.0, np.abs(ref).max())
+    indptr, indices, vals = (dv.to_device(a.indptr.astype(np.int32)), dv.to_device(a.indices.astype(np.int32)),
+                             dv.to_device(a.data))
+    xd = dv.to_device(x)
+    lens = np.diff(a.indptr)
+    long_rows = np.flatnonzero(lens > int(_native.load().pb200_spmv_long_row())).astype(np.int32)
+    # three row ranges with their own hub lists
+    y = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    for r0, r1 in ((0, 9_984), (9_984, 20_000), (20_000, n)):
+        mine = long_rows[(long_rows >= r0) & (long_rows < r1)]
+        dv.call("pb200_csr_spmv_rows_f64", indptr, indices, vals, n, a.nnz, r0, r1,
+                dv.to_device(mine) if len(mine) else None, len(mine), xd, y)
+    assert np.max(np.abs(y.cpu().numpy() - ref)) < 1e-12 * scale
+    # nonzero stream, whole matrix and the same three row ranges
+    tile = int(_native.load().pb200_csr_spmv_stream_tile())
+    n_tiles = -(-a.nnz // tile)
+    tile_lo = dv.empty((n_tiles + 1,), dv.I32)
+    head, tail = dv.zeros((n_tiles,), dv.F64), dv.zeros((n_tiles,), dv.F64)
+    dv.call("pb200_csr_spmv_stream_prepare", indptr, n, a.nnz, tile_lo)
+    tl = tile_lo.cpu().numpy()
+    assert np.array_equal(tl[:-1], np.searchsorted(a.indptr, np.arange(n_tiles) * tile, side="left")) and tl[-1] == n
+    y = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    dv.call("pb200_csr_spmv_stream_f64", indptr, indices, vals, n, a.nnz, tile_lo, head, tail, xd, y, 0, n, 0, n_tiles)
+    assert np.max(np.abs(y.cpu().numpy() - ref)) < 1e-12 * scale
+    y2 = torch.full((n,), float("nan"), dtype=torch.float64, device="cuda")
+    for r0, r1 in ((0, 9_984), (9_984, 20_000), (20_000, n)):
+        e0, e1 = int(a.indptr[r0]), int(a.indptr[r1])
+        dv.call("pb200_csr_spmv_stream_f64", indptr, indices, vals, n, a.nnz, tile_lo, head, tail, xd, y2, r0, r1,
+                e0 // tile, -(-e1 // tile))
+    assert torch.equal(y, y2)
+
+
+def test_row_sharded_eigensolver_pieces_reproduce_the_batched_steps(pb):
+    """pb200_csr_spmv_rows_f64 / pb200_csr_spmv_stream_f64 + pb200_lanczos_post_pro, step by step (what the row-sharded
+    eigensolver runs between its all-gathers), against pb200_lanczos_steps_pro on the same matrix and start vector."""
+    import torch
+    from palantir_b200 import _device as dv, _native
+
+    z = golden("dm_f32_n1500_d20.npz")
+    k = csr_matrix((z["k_data"], z["k_indices"], z["k_indptr"]), shape=(1500, 1500))
+    kd = dv.csr_from_host(k)
+    n, nnz, steps = 1500, kd.nnz, 120
+    tvals, svals, dis, dsq = dv.transition_and_symmetric(kd)
+    start = dv.to_device(np.random.default_rng(1).random(n))
+    nblk = n // 2048 + 1
+    tile = int(_native.load().pb200_csr_spmv_stream_tile())
+    n_tiles = -(-nnz // tile)
+    tile_lo = dv.empty((n_tiles + 1,), dv.I32)
+    head, tail = dv.zeros((n_tiles,), dv.F64), dv.zeros((n_tiles,), dv.F64)
+    dv.call("pb200_csr_spmv_stream_prepare", kd.indptr, n, nnz, tile_lo)
+
+    def run(mode):
+        V = dv.zeros((steps + 2, n), dv.F64)
+        alpha, beta = dv.zeros((steps + 2,), dv.F64), dv.zeros((steps + 3,), dv.F64)
+        w, h = dv.empty((n,), dv.F64), dv.empty((steps + 2,), dv.F64)
+        partial, tmp = dv.empty(((steps + 2) * nblk,), dv.F64), dv.empty((1,), dv.F64)
+        omstride = steps + 3
+        om = dv.zeros((3 * omstride,), dv.F64); om[0] = 1.0
+        gate, counters = dv.zeros((2,), dv.I32), dv.zeros((1,), dv.I32)
+        dv.call("pb200_lanczos_init", start, n, V, None, partial, tmp)
+        eps = 2.2e-16 * np.sqrt(n)
+        if mode == "batched":
+            dv.call("pb200_lanczos_steps_pro", kd.indptr, kd.indices, svals, n, nnz, None, 0, V, n, None, 0, 0, steps,
+                    alpha, beta, w, h, partial, tmp, om, omstride, gate, counters, eps, 1.5e-8)
+        else:
+            for j in range(steps):
+                if mode == "rows":
+                    for r0, r1 in ((0, 496), (496, 1008), (1008, n)):
+                        dv.call("pb200_csr_spmv_rows_f64", kd.indptr, kd.indices, svals, n, nnz, r0, r1, None, 0, V[j], w)
+                else:
+                    dv.call("pb200_csr_spmv_stream_f64", kd.indptr, kd.indices, svals, n, nnz, tile_lo, head, tail, V[j],
+                            w, 0, n, 0, n_tiles)
+                dv.call("pb200_lanczos_post_pro", n, V, n, j, alpha, beta, w, h, partial, tmp, om, omstride, gate,
+                        counters, eps, 1.5e-8)
+        return alpha.cpu().numpy()[:steps], beta.cpu().numpy()[1:steps + 1], V.cpu().numpy(), int(counters.item())
+
+    a0, b0, V0, c0 = run("batched")
+    a1, b1, V1, c1 = run("rows")
+    assert np.array_equal(a0, a1) and np.array_equal(b0, b1) and np.array_equal(V0, V1) and c0 == c1
+    # semi-orthogonal basis, and the tridiagonal matrix carries the leading eigenvalue of T (= 1)
+    G = V0[:steps] @ V0[:steps].T
+    assert np.abs(G - np.eye(steps)).max() < 1e-6
+    from scipy.linalg import eigh_tridiagonal
+    assert abs(eigh_tridiagonal(a0, b0[:-1], eigvals_only=True).max() - 1.0) < 1e-10
+    # the stream kernel sums a row in another order: same recurrence up to round-off
+    a2, b2, V2, c2 = run("stream")
+    assert np.abs(a2[:10] - a0[:10]).max() < 1e-12 and np.abs(b2[:10] - b0[:10]).max() < 1e-12
+    ev0 = eigh_tridiagonal(a0, b0[:-1], eigvals_only=True)[-3:]
+    ev2 = eigh_tridiagonal(a2, b2[:-1], eigvals_only=True)[-3:]
+    assert abs(ev2[-1] - 1.0) < 1e-10 and np.abs(ev2 - ev0).max() < 1e-8
+
+
 def test_windowed_spmv_and_relabelled_matrix_vs_scipy(pb):
     """The eigensolver's SpMV on the relabelled matrix (x window in shared memory) against scipy, on a
     matrix large enough to take the windowed kernel, with columns inside and far outside the window."""
