@@ -38,11 +38,12 @@ constexpr int TC_KC = 16;         // coordinates per ring stage (two MMA k-steps
 constexpr int TC_HALF = TC_BN * TC_KC * 4;      // bytes of one hi (or lo) block of a stage: 8 KB
 constexpr int TC_STAGE = 2 * TC_HALF;           // hi + lo: 16 KB
 constexpr int TC_KSTEP = TC_BN * 8 * 4;         // bytes of one k-step (8 coordinates) inside a block: 4 KB
-constexpr int TC_CAP = 128;       // candidate buffer entries per row (shared memory)
-constexpr int TC_LSTRIDE = TC_CAP + 1;   // row stride of the buffers in 64-bit words (odd: rows start on different banks)
-constexpr int TC_HIGH = TC_CAP - 32;     // a row above this is compacted before its thread may push (<= 32 pushes per step)
+constexpr int TC_CAP = 128;       // most candidate buffer entries per row (shared memory); the launch picks cap <= TC_CAP,
+                                  // row stride cap + 1 64-bit words (odd: rows start on different banks), and compacts a
+                                  // row above cap - 32 entries before its thread may push (<= 32 pushes per step)
 constexpr int TC_IDLE_MARGIN = 20;       // rows with more than k_keep + this many entries are compacted in idle time
-constexpr int TC_NST = 5;         // ring stages (16 KB each); the depth does not matter beyond 3 (measured)
+constexpr int TC_NST = 5;         // default ring stages (16 KB each)
+constexpr int TC_NST_MAX = 8;     // mbarrier slots
 constexpr int TC_MAX_KEEP = 48;
 constexpr int TC_NACC = 4;        // most TMEM accumulators in flight (what 512 columns minus the operand allow)
 constexpr int TC_THREADS = 192;   // 6 warps
@@ -60,6 +61,7 @@ struct TcParams {
   int d8;                 // coordinates rounded up to 8 (TMEM columns of one half of the query operand)
   int nacc;               // TMEM accumulators in flight: (512 - 2 d8) / 128, 2..4
   int k_keep;
+  int cap;                // candidate buffer entries per row (<= TC_CAP); the row stride is cap + 1 words
   int debug;              // dev only (PB200_TC_DEBUG): 1 = epilogue releases accumulators unread, 2 = no candidate pushes
   unsigned long long* lists;   // unused (kept for the ABI: the candidate buffers live in shared memory)
   int* out_idx;
@@ -169,9 +171,9 @@ __device__ __forceinline__ int tc_tile_of(int s, int q, int T) {
 // smallest 32-bit key is found by a bitwise search below the keys' common prefix (one warp reduction per
 // bit), then the survivors are written back by ballot-prefix positions -- no ranking: the order inside
 // the buffer is irrelevant until the final emit.
-__device__ __noinline__ void tc_compact_row(TcCtl* ctl, unsigned long long* buf, int row, int k_keep, int lane) {
+__device__ __noinline__ void tc_compact_row(TcCtl* ctl, unsigned long long* buf, int row, int k_keep, int lane, int cap) {
   int c = ctl->cnt[row];
-  c = c < TC_CAP ? c : TC_CAP;
+  c = c < cap ? c : cap;
   if (c <= k_keep) return;
   unsigned long long e[4];
   uint32_t key[4];
@@ -227,7 +229,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
   // [B ring: nst stages][candidate buffers 128 x TC_LSTRIDE words][control]; the query operand lives in TMEM
   unsigned char* b_smem = smem_raw;
   unsigned long long* lists = reinterpret_cast<unsigned long long*>(b_smem + (size_t)p.nst * TC_STAGE);
-  TcCtl& ctl = *reinterpret_cast<TcCtl*>(lists + TC_BM * TC_LSTRIDE);
+  const int CAP = p.cap, LSTRIDE = p.cap + 1, HIGH = p.cap - 32;
+  TcCtl& ctl = *reinterpret_cast<TcCtl*>(lists + TC_BM * LSTRIDE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qbase = p.q0 + blockIdx.x * TC_BM;
   const int row_local0 = blockIdx.x * TC_BM;
@@ -403,7 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
     // ================= epilogue (warps 2..5): TMEM lane quarter = warp % 4 =================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;           // CTA-local query row owned by this thread
-    unsigned long long* mybuf = lists + row * TC_LSTRIDE;
+    unsigned long long* mybuf = lists + row * LSTRIDE;
     bool compacted_any = false;
     int c = 0;                                     // entries in this row's buffer (shared copy written before compactions)
     {
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         const int l = __ffs(fuller) - 1;
         ctl.cnt[row] = c;
         __syncwarp();
-        tc_compact_row(&ctl, lists + (quarter * 32 + l) * TC_LSTRIDE, quarter * 32 + l, p.k_keep, lane);
+        tc_compact_row(&ctl, lists + (quarter * 32 + l) * LSTRIDE, quarter * 32 + l, p.k_keep, lane, CAP);
         c = ctl.cnt[row];
         compacted_any = true;
       }
@@ -478,13 +481,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         const float m = fminf(fminf(fminf(q[0], q[1]), fminf(q[2], q[3])), fminf(fminf(q[4], q[5]), fminf(q[6], q[7])));
         if (__any_sync(0xffffffffu, m < thr) && p.debug != 2) {
           // room for this step's (at most 32) pushes: rows above TC_HIGH are compacted first
-          const unsigned need = __ballot_sync(0xffffffffu, c > TC_HIGH);
+          const unsigned need = __ballot_sync(0xffffffffu, c > HIGH);
           if (need) {
             ctl.cnt[row] = c;
             __syncwarp();
             for (unsigned mm = need; mm; mm &= mm - 1) {
               const int l = __ffs(mm) - 1;
-              tc_compact_row(&ctl, lists + (quarter * 32 + l) * TC_LSTRIDE, quarter * 32 + l, p.k_keep, lane);
+              tc_compact_row(&ctl, lists + (quarter * 32 + l) * LSTRIDE, quarter * 32 + l, p.k_keep, lane, CAP);
             }
             compacted_any = true;
             thr = ctl.thr[row];
@@ -545,10 +548,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       const int r = quarter * 32 + l;
       const int grow = row_local0 + r;
       if (grow >= p.nq) continue;
-      tc_compact_row(&ctl, lists + r * TC_LSTRIDE, r, p.k_keep, lane);   // leaves <= k_keep <= 48 entries
+      tc_compact_row(&ctl, lists + r * LSTRIDE, r, p.k_keep, lane, CAP);   // leaves <= k_keep <= 48 entries
       int c = ctl.cnt[r];
       c = c < 64 ? c : 64;
-      const unsigned long long* buf = lists + r * TC_LSTRIDE;
+      const unsigned long long* buf = lists + r * LSTRIDE;
       const unsigned long long e0 = lane < c ? buf[lane] : ~0ull;
       const unsigned long long e1 = lane + 32 < c ? buf[lane + 32] : ~0ull;
       int q0r = 0, q1r = 0;
@@ -728,10 +731,14 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   p.nacc = (512 - 2 * d8) / TC_BN;
   if (p.nacc > TC_NACC) p.nacc = TC_NACC;
   { const char* e = getenv("PB200_TC_NACC"); if (e && atoi(e) >= 1 && atoi(e) < p.nacc) p.nacc = atoi(e); }   // dev: fewer accumulators
-  int nst = TC_NST;
-  { const char* e = getenv("PB200_TC_NST"); if (e && atoi(e) >= 2 && atoi(e) < nst) nst = atoi(e); }
+  // ring depth and candidate buffer size share the shared memory: nst * 16 KB + 128 * (cap + 1) * 8 B + control <= 227 KB
+  int nst = TC_NST, cap = TC_CAP;
+  { const char* e = getenv("PB200_TC_NST"); if (e && atoi(e) >= 2 && atoi(e) <= TC_NST_MAX) nst = atoi(e); }
+  { const char* e = getenv("PB200_TC_CAP"); if (e && atoi(e) >= k_keep + 33 && atoi(e) <= TC_CAP) cap = atoi(e); }
   p.nst = nst;
-  const int smem = nst * TC_STAGE + TC_BM * TC_LSTRIDE * 8 + (int)sizeof(TcCtl) + 64;
+  p.cap = cap;
+  const int smem = nst * TC_STAGE + TC_BM * (cap + 1) * 8 + (int)sizeof(TcCtl) + 64;
+  if (smem > 227 * 1024) { set_error_msg("pb200_knn_candidates_tc: ring depth x candidate buffers exceed shared memory"); return -1; }
   PB_CHECK(cudaFuncSetAttribute(knn_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   knn_candidates_tc_kernel<<<div_up(nq, TC_BM), TC_THREADS, smem, st>>>(p);
   PB_CHECK_LAUNCH("knn_candidates_tc_kernel");

@@ -1,0 +1,27 @@
+"""tcgen05 kNN candidate kernel: ring depth against candidate-buffer size (they share the 227 KB of shared memory),
+at benchmark size (dev tool).  PB200_TC_NST / PB200_TC_CAP are read by the library at every launch."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from palantir_b200 import _device as dv
+from palantir_b200.datasets import synth_branching
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+x, _ = synth_branching(n, 100)
+xd = dv.to_device(x)
+prep = dv.knn_prepare(xd)
+ref = None
+for nst, cap in ((5, 128), (3, 128), (2, 128), (6, 112), (7, 96), (8, 80), (5, 96), (5, 128)):
+    os.environ["PB200_TC_NST"], os.environ["PB200_TC_CAP"] = str(nst), str(cap)
+    ts = []
+    for rep in range(3):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        idx, dist, st = dv.knn_expanded(prep, 31)
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    same = True if ref is None else bool(torch.equal(idx, ref[0]) and torch.equal(dist, ref[1]))
+    if ref is None:
+        ref = (idx.clone(), dist.clone())
+    print(f"ring {nst} x 16 KB, buffers {cap}: knn_expanded {min(ts):.1f} ms (runs {[round(t, 1) for t in ts]}); "
+          f"tiles visited {st.get('tiles_visited_frac')}, flagged rows {st.get('flagged')}; same result {same}", flush=True)
