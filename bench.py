@@ -236,7 +236,8 @@ SSSP_STAGES = ("sssp_partition", "sssp_tables", "sssp_overlay", "sssp", "sssp_ex
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
 # these kernels on the config-3 workload at one GPU (profiles/): kernel -> (bytes, file)
 NCU_TRAFFIC_C3 = {
-    "knn_candidates_tc_kernel": (1.513e11, "profiles/r1_knn_candidates_ncu.md"),
+    "knn_candidates_tc_kernel": (1.706e11, "profiles/r2_knn_tc_ncu.md"),
+    "csr_spmv_stream_kernel": (6.617e8, "profiles/r2_spmv_ncu.md"),
 }
 
 
@@ -498,7 +499,11 @@ def run_gpu_arm(args):
               "spmv": spmv_ms * (utils.LAST_INFO.get("lanczos") or {}).get("steps", 0)}
     dominant = max(shares, key=shares.get)
     spmv_roof = {"bound": "hbm", "kernel": spmv_kernel,
-                 "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": None,
+                 "achieved": spmv_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
+                 "traffic": (NCU_TRAFFIC_C3["csr_spmv_stream_kernel"][0]
+                             if (dv.SPMV_STREAM and n == 1_000_000 and d == 100) else None),
+                 "traffic_source": (NCU_TRAFFIC_C3["csr_spmv_stream_kernel"][1]
+                                    if (dv.SPMV_STREAM and n == 1_000_000 and d == 100) else None),
                  "peak_source": hbm_src, "algorithmic": "12*nnz + 4*(N+1) + 16*N bytes per launch",
                  "ms_per_launch": spmv_ms, "row_order": spmv_order, "row_kernels_ms_per_launch": spmv_rows_ms,
                  "share_of_step": shares["spmv"] / ms_step,

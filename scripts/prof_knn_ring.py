@@ -9,6 +9,26 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 x, _ = synth_branching(n, 100)
 xd = dv.to_device(x)
 prep = dv.knn_prepare(xd)
+if os.environ.get("PB200_TC_DEBUG"):
+    # a debug mode of the kernel (1 = accumulators released unread, 2 = no candidate pushes): candidate kernel alone
+    kk = 43
+    cand = dv.empty((n, kk), dv.I32); score = dv.empty((n, kk), dv.F32); thr = dv.empty((n,), dv.F32)
+    lists = dv.empty((256,), dv.I64); vis = dv.zeros((1,), dv.I64)
+    for nst, cap in ((5, 80), (2, 80), (3, 80), (4, 80), (6, 80), (8, 80)):
+        os.environ["PB200_TC_NST"], os.environ["PB200_TC_CAP"] = str(nst), str(cap)
+        ts = []
+        for rep in range(3):
+            vis.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dv.call("pb200_knn_candidates_tc", prep.xtc, prep.ld, prep.yn, prep.xcn, prep.box_lo, prep.box_hi, 0, n,
+                    prep.d, kk, lists, cand, score, thr, vis)
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        tiles = float(vis.item())
+        tf = 3 * 2 * 128 * 128 * 104 * tiles / (min(ts) * 1e-3) / 1e12
+        print(f"debug {os.environ['PB200_TC_DEBUG']}: ring {nst}: candidate kernel {min(ts):.1f} ms, {tiles:.3e} tiles, {tf:.0f} TFLOP/s executed", flush=True)
+    sys.exit(0)
 ref = None
 for nst, cap in ((5, 128), (3, 128), (2, 128), (6, 112), (7, 96), (8, 80), (5, 96), (5, 128)):
     os.environ["PB200_TC_NST"], os.environ["PB200_TC_CAP"] = str(nst), str(cap)
