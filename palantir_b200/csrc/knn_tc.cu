@@ -62,7 +62,9 @@ struct TcParams {
   int nacc;               // TMEM accumulators in flight: (512 - 2 d8) / 128, 2..4
   int k_keep;
   int cap;                // candidate buffer entries per row (<= TC_CAP); the row stride is cap + 1 words
-  int debug;              // dev only (PB200_TC_DEBUG): 1 = epilogue releases accumulators unread, 2 = no candidate pushes
+  int slack;              // in-stream compactions keep k_keep .. k_keep + slack entries (0: exactly k_keep)
+  int debug;              // dev only (PB200_TC_DEBUG): 1 = epilogue releases accumulators unread, 2 = no candidate pushes,
+                          // 3 = accumulators read (tcgen05.ld) but not processed
   unsigned long long* lists;   // unused (kept for the ABI: the candidate buffers live in shared memory)
   int* out_idx;
   float* out_score;
@@ -224,6 +226,74 @@ __device__ __noinline__ void tc_compact_row(TcCtl* ctl, unsigned long long* buf,
   __syncwarp();
 }
 
+// The compaction used while the tiles stream by: it stops the bitwise search as soon as the bucket of keys still
+// undecided holds at most `slack` entries beyond the k_keep-th, keeps everything below the bucket's top (between
+// k_keep and k_keep + slack entries) and makes that top the row's threshold.  The threshold is then an upper bound of
+// the k_keep-th smallest score instead of the score itself -- every entry dropped or never pushed still has k_keep kept
+// entries that are no larger, which is all the exact final selection (tc_compact_row at the end) and the re-rank's
+// certificate need -- and the search takes ~3-6 warp reductions instead of ~22 (the keys of a row share their leading
+// bits; ncu: the exact routine was 13 % of the epilogue warps' time, and a compaction in progress delays the next
+// accumulator by up to its whole length).  Many equal keys (the search runs out of bits): the exact routine.
+__device__ __noinline__ void tc_compact_row_fast(TcCtl* ctl, unsigned long long* buf, int row, int k_keep, int lane, int cap,
+                                                 int slack) {
+  int c = ctl->cnt[row];
+  c = c < cap ? c : cap;
+  if (c <= k_keep + slack) return;
+  unsigned long long e[4];
+  uint32_t key[4];
+  uint32_t mn = 0xffffffffu, mx = 0u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = lane + 32 * q;
+    e[q] = i < c ? buf[i] : ~0ull;
+    key[q] = (uint32_t)(e[q] >> 32);
+    mn = key[q] < mn ? key[q] : mn;
+    if (i < c) mx = key[q] > mx ? key[q] : mx;
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  bool done = false;
+  uint32_t top = 0u;
+  int hi_cnt = c;
+  if (mn != mx) {
+    const int hb = 31 - __clz(mn ^ mx);
+    uint32_t piv = hb == 31 ? 0u : (mn & ~((2u << hb) - 1u));
+    for (int b = hb; b >= 0; --b) {
+      const uint32_t cand = piv | (1u << b);
+      const int cl = (int)(key[0] < cand) + (int)(key[1] < cand) + (int)(key[2] < cand) + (int)(key[3] < cand);
+      const int tot = (int)__reduce_add_sync(0xffffffffu, (unsigned)cl);
+      if (tot < k_keep) {
+        piv = cand;
+      } else {
+        top = cand;
+        hi_cnt = tot;
+        if (hi_cnt <= k_keep + slack) { done = true; break; }
+      }
+    }
+  }
+  if (!done) {
+    __syncwarp();
+    tc_compact_row(ctl, buf, row, k_keep, lane, cap);
+    return;
+  }
+  // keep the hi_cnt entries below `top`
+  const unsigned lt = (1u << lane) - 1u;
+  int base = 0;
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const bool keep = key[q] < top;
+    const unsigned bl = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[base + __popc(bl & lt)] = e[q];
+    base += __popc(bl);
+  }
+  if (lane == 0) {
+    ctl->thr[row] = f32_from_ordered(top);
+    ctl->cnt[row] = hi_cnt;
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // [B ring: nst stages][candidate buffers 128 x TC_LSTRIDE words][control]; the query operand lives in TMEM
@@ -268,7 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
 
   if (warp == 0) {
     // ================= producer =================
-    int cursor = 0, st = 0, tslot = 0;     // st / ph (ring slot and pass parity) live in lane 0
+    int cursor = 0, st = 0, tslot = 0;     // st / ph (ring slot and pass parity) live in the issuing lane
     uint32_t ph = 0;
     unsigned long long visited = 0;
     // Tile choice, 32 candidates of the outward sequence per step (one per lane): the squared gap between
@@ -318,9 +388,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         mask &= mask - 1;
         chosen = tc_tile_of(mask_base + bit, qtile, T);
       }
+      // The copies are issued by ONE lane chosen with elect.sync (always the same lane for a full warp): under
+      // `if (lane == 0)` nvcc wraps every UBLKCP in an ELECT ... R2UR.BROADCAST ... BRA.U.ANY loop over the active
+      // lanes, and the issuing lane's own instruction stream (~70 instructions per 16 KB stage) was what bounded
+      // the whole pipeline (ncu: the producer never waits for a free slot, the MMA thread waits for data).
+      const bool issuer = tc_elect_one();
       if (chosen < 0) {
         // end of stream
-        if (lane == 0) {
+        if (issuer) {
           mbar_wait(&ctl.b_empty[st], ph ^ 1u);
           ctl.tile_ring[tslot] = -1;
           mbar_arrive(&ctl.b_full[st]);
@@ -328,24 +403,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         break;
       }
       ++visited;
-      if (lane == 0) {
+      if (issuer) {
         ctl.tile_ring[tslot] = chosen;           // published by the release of the first stage's arrive
         const float* src = p.xtc + (long long)chosen * KCH * (TC_STAGE / 4);
-        for (int kc = 0; kc < KCH; ++kc) {
+        const int full = p.tail_steps == 2 ? KCH : KCH - 1;      // stages copied whole
+        for (int kc = 0; kc < full; ++kc) {
           mbar_wait(&ctl.b_empty[st], ph ^ 1u);
-          unsigned char* dst = b_smem + (size_t)st * TC_STAGE;
-          if (kc < KCH - 1 || p.tail_steps == 2) {
-            mbar_arrive_expect_tx(&ctl.b_full[st], TC_STAGE);
-            bulk_g2s(dst, src, TC_STAGE, &ctl.b_full[st]);
-          } else {
-            mbar_arrive_expect_tx(&ctl.b_full[st], 2 * last_bytes);
-            bulk_g2s(dst, src, last_bytes, &ctl.b_full[st]);
-            bulk_g2s(dst + TC_HALF, src + TC_HALF / 4, last_bytes, &ctl.b_full[st]);
-          }
+          mbar_arrive_expect_tx(&ctl.b_full[st], TC_STAGE);
+          bulk_g2s(b_smem + (size_t)st * TC_STAGE, src, TC_STAGE, &ctl.b_full[st]);
           src += TC_STAGE / 4;
           if (++st == NST) { st = 0; ph ^= 1u; }
         }
+        if (full < KCH) {
+          // last stage of a tile with d8 % 16 == 8: one k-step of hi, one of lo
+          mbar_wait(&ctl.b_empty[st], ph ^ 1u);
+          unsigned char* dst = b_smem + (size_t)st * TC_STAGE;
+          mbar_arrive_expect_tx(&ctl.b_full[st], 2 * last_bytes);
+          bulk_g2s(dst, src, last_bytes, &ctl.b_full[st]);
+          bulk_g2s(dst + TC_HALF, src + TC_HALF / 4, last_bytes, &ctl.b_full[st]);
+          if (++st == NST) { st = 0; ph ^= 1u; }
+        }
       }
+      __syncwarp();
       tslot = (tslot + 1) & 15;
     }
     if (lane == 0 && p.tiles_visited) atomicAdd(p.tiles_visited, visited);
@@ -444,7 +523,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         const int l = __ffs(fuller) - 1;
         ctl.cnt[row] = c;
         __syncwarp();
-        tc_compact_row(&ctl, lists + (quarter * 32 + l) * LSTRIDE, quarter * 32 + l, p.k_keep, lane, CAP);
+        tc_compact_row_fast(&ctl, lists + (quarter * 32 + l) * LSTRIDE, quarter * 32 + l, p.k_keep, lane, CAP, p.slack);
         c = ctl.cnt[row];
         compacted_any = true;
       }
@@ -466,6 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       float thr = ctl.thr[row];
       const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN);
       auto process = [&](uint32_t (&v)[32], const int cb) {
+        if (p.debug == 3) return;                    // dev: accumulators read from tensor memory, nothing else
         float q[8];                                  // minimum of each group of four columns
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -487,7 +567,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
             __syncwarp();
             for (unsigned mm = need; mm; mm &= mm - 1) {
               const int l = __ffs(mm) - 1;
-              tc_compact_row(&ctl, lists + (quarter * 32 + l) * LSTRIDE, quarter * 32 + l, p.k_keep, lane, CAP);
+              tc_compact_row_fast(&ctl, lists + (quarter * 32 + l) * LSTRIDE, quarter * 32 + l, p.k_keep, lane, CAP, p.slack);
             }
             compacted_any = true;
             thr = ctl.thr[row];
@@ -737,6 +817,8 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   { const char* e = getenv("PB200_TC_CAP"); if (e && atoi(e) >= k_keep + 33 && atoi(e) <= TC_CAP) cap = atoi(e); }
   p.nst = nst;
   p.cap = cap;
+  p.slack = 4;                                     // < TC_IDLE_MARGIN, so that an idle-time compaction always shrinks its row (0 / 4 / 8 / 12: 152.0 / 148.4 / 149.9 / 150.4 ms at config 3)
+  { const char* e = getenv("PB200_TC_SLACK"); if (e && atoi(e) >= 0 && atoi(e) < TC_IDLE_MARGIN) p.slack = atoi(e); }
   const int smem = nst * TC_STAGE + TC_BM * (cap + 1) * 8 + (int)sizeof(TcCtl) + 64;
   if (smem > 227 * 1024) { set_error_msg("pb200_knn_candidates_tc: ring depth x candidate buffers exceed shared memory"); return -1; }
   PB_CHECK(cudaFuncSetAttribute(knn_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

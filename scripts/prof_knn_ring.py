@@ -14,7 +14,8 @@ if os.environ.get("PB200_TC_DEBUG"):
     kk = 43
     cand = dv.empty((n, kk), dv.I32); score = dv.empty((n, kk), dv.F32); thr = dv.empty((n,), dv.F32)
     lists = dv.empty((256,), dv.I64); vis = dv.zeros((1,), dv.I64)
-    for nst, cap in ((5, 80), (2, 80), (3, 80), (4, 80), (6, 80), (8, 80)):
+    rings = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [5, 2, 3, 4, 6, 8]
+    for nst, cap in [(r, 128 if r <= 5 else 80) for r in rings]:
         os.environ["PB200_TC_NST"], os.environ["PB200_TC_CAP"] = str(nst), str(cap)
         ts = []
         for rep in range(3):
@@ -30,8 +31,11 @@ if os.environ.get("PB200_TC_DEBUG"):
         print(f"debug {os.environ['PB200_TC_DEBUG']}: ring {nst}: candidate kernel {min(ts):.1f} ms, {tiles:.3e} tiles, {tf:.0f} TFLOP/s executed", flush=True)
     sys.exit(0)
 ref = None
-for nst, cap in ((5, 128), (3, 128), (2, 128), (6, 112), (7, 96), (8, 80), (5, 96), (5, 128)):
-    os.environ["PB200_TC_NST"], os.environ["PB200_TC_CAP"] = str(nst), str(cap)
+configs = [(5, 128, 8), (5, 128, 0), (5, 128, 4), (5, 128, 12), (5, 128, 16), (6, 112, 12), (5, 128, 8)]
+if len(sys.argv) > 2:
+    configs = [tuple(int(v) for v in c.split(":")) for c in sys.argv[2].split(",")]
+for nst, cap, slack in configs:
+    os.environ["PB200_TC_NST"], os.environ["PB200_TC_CAP"], os.environ["PB200_TC_SLACK"] = str(nst), str(cap), str(slack)
     ts = []
     for rep in range(3):
         torch.cuda.synchronize()
@@ -43,5 +47,5 @@ for nst, cap in ((5, 128), (3, 128), (2, 128), (6, 112), (7, 96), (8, 80), (5, 9
     same = True if ref is None else bool(torch.equal(idx, ref[0]) and torch.equal(dist, ref[1]))
     if ref is None:
         ref = (idx.clone(), dist.clone())
-    print(f"ring {nst} x 16 KB, buffers {cap}: knn_expanded {min(ts):.1f} ms (runs {[round(t, 1) for t in ts]}); "
+    print(f"ring {nst} x 16 KB, buffers {cap}, slack {slack}: knn_expanded {min(ts):.1f} ms (runs {[round(t, 1) for t in ts]}); "
           f"tiles visited {st.get('tiles_visited_frac')}, flagged rows {st.get('flagged')}; same result {same}", flush=True)
