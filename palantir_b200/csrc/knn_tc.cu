@@ -63,6 +63,7 @@ struct TcParams {
   int k_keep;
   int cap;                // candidate buffer entries per row (<= TC_CAP); the row stride is cap + 1 words
   int slack;              // in-stream compactions keep k_keep .. k_keep + slack entries (0: exactly k_keep)
+  int idle_margin;        // rows with more than k_keep + this many entries are compacted in idle time (> slack)
   int debug;              // dev only (PB200_TC_DEBUG): 1 = epilogue releases accumulators unread, 2 = no candidate pushes,
                           // 3 = accumulators read (tcgen05.ld) but not processed
   unsigned long long* lists;   // unused (kept for the ABI: the candidate buffers live in shared memory)
@@ -518,7 +519,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       // the next accumulator is not ready: use the time to compact this warp's fuller rows (tighter
       // thresholds earlier, and no bursts of compactions on the critical path later)
       while (!__all_sync(0xffffffffu, mbar_test(&ctl.acc_full[buf], accph))) {
-        const unsigned fuller = __ballot_sync(0xffffffffu, c > p.k_keep + TC_IDLE_MARGIN);
+        const unsigned fuller = __ballot_sync(0xffffffffu, c > p.k_keep + p.idle_margin);
         if (!fuller) break;
         const int l = __ffs(fuller) - 1;
         ctl.cnt[row] = c;
@@ -818,7 +819,10 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   p.nst = nst;
   p.cap = cap;
   p.slack = 4;                                     // < TC_IDLE_MARGIN, so that an idle-time compaction always shrinks its row (0 / 4 / 8 / 12: 152.0 / 148.4 / 149.9 / 150.4 ms at config 3)
-  { const char* e = getenv("PB200_TC_SLACK"); if (e && atoi(e) >= 0 && atoi(e) < TC_IDLE_MARGIN) p.slack = atoi(e); }
+  p.idle_margin = TC_IDLE_MARGIN;
+  { const char* e = getenv("PB200_TC_IDLE"); if (e && atoi(e) >= 1 && atoi(e) <= 64) p.idle_margin = atoi(e); }
+  { const char* e = getenv("PB200_TC_SLACK"); if (e && atoi(e) >= 0 && atoi(e) < p.idle_margin) p.slack = atoi(e); }
+  if (p.slack >= p.idle_margin) p.slack = p.idle_margin - 1;
   const int smem = nst * TC_STAGE + TC_BM * (cap + 1) * 8 + (int)sizeof(TcCtl) + 64;
   if (smem > 227 * 1024) { set_error_msg("pb200_knn_candidates_tc: ring depth x candidate buffers exceed shared memory"); return -1; }
   PB_CHECK(cudaFuncSetAttribute(knn_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -34,8 +34,11 @@ ref = None
 configs = [(5, 128, 8), (5, 128, 0), (5, 128, 4), (5, 128, 12), (5, 128, 16), (6, 112, 12), (5, 128, 8)]
 if len(sys.argv) > 2:
     configs = [tuple(int(v) for v in c.split(":")) for c in sys.argv[2].split(",")]
-for nst, cap, slack in configs:
+for cfg in configs:
+    nst, cap, slack = cfg[:3]
+    idle = cfg[3] if len(cfg) > 3 else 20
     os.environ["PB200_TC_NST"], os.environ["PB200_TC_CAP"], os.environ["PB200_TC_SLACK"] = str(nst), str(cap), str(slack)
+    os.environ["PB200_TC_IDLE"] = str(idle)
     ts = []
     for rep in range(3):
         torch.cuda.synchronize()
@@ -47,5 +50,5 @@ for nst, cap, slack in configs:
     same = True if ref is None else bool(torch.equal(idx, ref[0]) and torch.equal(dist, ref[1]))
     if ref is None:
         ref = (idx.clone(), dist.clone())
-    print(f"ring {nst} x 16 KB, buffers {cap}, slack {slack}: knn_expanded {min(ts):.1f} ms (runs {[round(t, 1) for t in ts]}); "
+    print(f"ring {nst} x 16 KB, buffers {cap}, slack {slack}, idle margin {idle}: knn_expanded {min(ts):.1f} ms (runs {[round(t, 1) for t in ts]}); "
           f"tiles visited {st.get('tiles_visited_frac')}, flagged rows {st.get('flagged')}; same result {same}", flush=True)
