@@ -64,7 +64,6 @@ struct TcParams {
   int cap;                // candidate buffer entries per row (<= TC_CAP); the row stride is cap + 1 words
   int slack;              // in-stream compactions keep k_keep .. k_keep + slack entries (0: exactly k_keep)
   int idle_margin;        // rows with more than k_keep + this many entries are compacted in idle time (> slack)
-  int early_release;      // epilogue: whole accumulator into registers, released before it is processed
   int debug;              // dev only (PB200_TC_DEBUG): 1 = epilogue releases accumulators unread, 2 = no candidate pushes,
                           // 3 = accumulators read (tcgen05.ld) but not processed
   unsigned long long* lists;   // unused (kept for the ABI: the candidate buffers live in shared memory)
@@ -548,6 +547,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * TC_BN);
       auto process = [&](uint32_t (&v)[32], const int cb) {
         if (p.debug == 3) return;                    // dev: accumulators read from tensor memory, nothing else
+        if (p.debug == 4 && cb >= 2) return;         // dev: only half of the columns processed (wrong results; timing only)
         float q[8];                                  // minimum of each group of four columns
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -595,27 +595,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
           }
         }
       };
-      if (p.early_release) {
-        // All four 32-column blocks of the accumulator into registers first (128 values per thread: one CTA per SM
-        // leaves 341 registers per thread), then the accumulator goes back to the MMA issuer BEFORE anything is
-        // processed: it is held for four tensor-memory loads instead of three quarters of the epilogue.
-        uint32_t v0[32], v1[32], v2[32], v3[32];
-        tc_ld32_issue(tbase, v0);
-        tc_ld32_issue(tbase + 32u, v1);
-        tc_ld32_issue(tbase + 64u, v2);
-        tc_ld32_issue(tbase + 96u, v3);
-        tc_ld32_wait(v0);
-        tc_ld32_wait(v1);
-        tc_ld32_wait(v2);
-        tc_ld32_wait(v3);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctl.acc_empty[buf]);
-        process(v0, 0);
-        process(v1, 1);
-        process(v2, 2);
-        process(v3, 3);
-      } else {
+      // (Measured and dropped: all four blocks into registers first and the accumulator released before anything is
+      // processed -- 163.4 ms against 149.5 ms for the kNN call: the tensor-memory loads no longer overlap the
+      // processing, and the time the accumulator is held was not what the MMA issuer waits for.)
+      {
         uint32_t va[32], vb[32];
         tc_ld32_issue(tbase, va);
 #pragma unroll 1
@@ -840,8 +823,6 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   p.nst = nst;
   p.cap = cap;
   p.slack = 4;                                     // < TC_IDLE_MARGIN, so that an idle-time compaction always shrinks its row (0 / 4 / 8 / 12: 152.0 / 148.4 / 149.9 / 150.4 ms at config 3)
-  p.early_release = 1;
-  { const char* e = getenv("PB200_TC_EARLY"); if (e) p.early_release = atoi(e) != 0; }
   p.idle_margin = TC_IDLE_MARGIN;
   { const char* e = getenv("PB200_TC_IDLE"); if (e && atoi(e) >= 1 && atoi(e) <= 64) p.idle_margin = atoi(e); }
   { const char* e = getenv("PB200_TC_SLACK"); if (e && atoi(e) >= 0 && atoi(e) < p.idle_margin) p.slack = atoi(e); }

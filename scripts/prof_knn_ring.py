@@ -9,7 +9,23 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 x, _ = synth_branching(n, 100)
 xd = dv.to_device(x)
 prep = dv.knn_prepare(xd)
-if os.environ.get("PB200_TC_DEBUG"):
+if os.environ.get("PB200_TC_DEBUG") == "4":
+    # half of the columns processed: wrong candidates, but thresholds still tighten and tiles are still pruned
+    kk = 43
+    cand = dv.empty((n, kk), dv.I32); score = dv.empty((n, kk), dv.F32); thr = dv.empty((n,), dv.F32)
+    lists = dv.empty((256,), dv.I64); vis = dv.zeros((1,), dv.I64)
+    for rep in range(3):
+        vis.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dv.call("pb200_knn_candidates_tc", prep.xtc, prep.ld, prep.yn, prep.xcn, prep.box_lo, prep.box_hi, 0, n,
+                prep.d, kk, lists, cand, score, thr, vis)
+        e1.record(); torch.cuda.synchronize()
+        tiles = float(vis.item())
+        print(f"debug 4: candidate kernel {e0.elapsed_time(e1):.1f} ms, {tiles:.3e} tiles, "
+              f"{3 * 2 * 128 * 128 * 104 * tiles / (e0.elapsed_time(e1) * 1e-3) / 1e12:.0f} TFLOP/s executed", flush=True)
+    sys.exit(0)
+if os.environ.get("PB200_TC_DEBUG", "0") != "0":
     # a debug mode of the kernel (1 = accumulators released unread, 2 = no candidate pushes): candidate kernel alone
     kk = 43
     cand = dv.empty((n, kk), dv.I32); score = dv.empty((n, kk), dv.F32); thr = dv.empty((n,), dv.F32)
