@@ -664,6 +664,8 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
     info = {"converged": False}
     theta = yvec = None
     step_batch = batch
+    lagged = bool(stream_spmv and batch > 5)          # large problems: convergence checks one batch behind the device
+    pending = None
     while m < max_basis:
         steps = min(step_batch, max_basis - m)
         if m + steps > cap:
@@ -701,26 +703,57 @@ def lanczos_topk(kern: DeviceCSR, svals: torch.Tensor, dis: torch.Tensor, start:
         m += steps
         if m < k + 1 and m < max_basis:
             continue
-        a = alpha[:m].cpu().numpy()
-        b = beta[1:m + 1].cpu().numpy()          # b[j] = beta_{j+1}
-        theta_all, y_all = eigh_tridiagonal(a, b[:m - 1])
-        order = np.argsort(-np.abs(theta_all))[:k]
-        resid = np.abs(b[m - 1] * y_all[m - 1, order])
-        theta, yvec = theta_all[order], y_all[:, order]
-        info.update(steps=m, max_resid=float(resid.max()))
-        info.setdefault("history", []).append((m, float(resid.max())))
-        # the residuals fall by orders of magnitude over the last ten steps (1e-4 -> 1e-9 -> 1e-15 at 1 M cells):
-        # once they are small, look every five steps instead of every twenty
-        if resid.max() < 1e-3 * max(1e-3, np.abs(theta).max()):
-            step_batch = max(1, min(batch, 5))
-        exhausted = (m >= n) or (b[m - 1] <= 1e-14 * max(1.0, np.abs(theta_all).max()))
-        done = bool(np.all(resid <= tol * np.maximum(np.abs(theta), 1e-3)) or exhausted)
-        if sharded:
-            # the ranks run identical kernels on identical data, so they agree; rank 0's word is taken anyway,
-            # because a disagreement would leave the all-gathers of the next batch unmatched
-            ctl = torch.tensor([int(done), step_batch], dtype=torch.int64, device=V.device)
-            _dist.broadcast_(ctl)
-            done, step_batch = bool(ctl[0].item()), int(ctl[1].item())
+        looks = []
+        if lagged and step_batch == batch and m < max_basis:
+            # Far from convergence (20-step batches): the coefficients of this batch go to the host asynchronously and
+            # the host looks at the PREVIOUS batch while the device runs this one -- the m x m eigenproblem (~1 ms at
+            # m = 200) and the two read-backs no longer stall the stream a dozen times per solve.
+            a_h = torch.empty((m,), dtype=F64, pin_memory=True)
+            b_h = torch.empty((m,), dtype=F64, pin_memory=True)
+            a_h.copy_(alpha[:m], non_blocking=True)
+            b_h.copy_(beta[1:m + 1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            prev, pending = pending, (m, a_h, b_h, ev)
+            if prev is None:
+                continue
+            looks.append(prev)
+        looks.append(None)                            # the batch just run (skipped while the previous one looks far off)
+        done = False
+        for look in looks:
+            if look is not None:
+                m_chk, a_t, b_t, ev_prev = look
+                ev_prev.synchronize()
+                a, b = a_t.numpy(), b_t.numpy()
+            else:
+                if len(looks) == 2 and step_batch == batch:
+                    break                             # still far from convergence: keep running one batch ahead
+                pending = None
+                m_chk = m
+                a = alpha[:m].cpu().numpy()
+                b = beta[1:m + 1].cpu().numpy()          # b[j] = beta_{j+1}
+            theta_all, y_all = eigh_tridiagonal(a, b[:m_chk - 1])
+            order = np.argsort(-np.abs(theta_all))[:k]
+            resid = np.abs(b[m_chk - 1] * y_all[m_chk - 1, order])
+            theta, yvec = theta_all[order], y_all[:, order]
+            info.update(steps=m_chk, max_resid=float(resid.max()))
+            info.setdefault("history", []).append((m_chk, float(resid.max())))
+            # the residuals fall by orders of magnitude over the last ten steps (1e-4 -> 1e-9 -> 1e-15 at 1 M cells):
+            # once they are small, look every five steps instead of every twenty (and at the batch just run)
+            if resid.max() < 1e-3 * max(1e-3, np.abs(theta).max()):
+                step_batch = max(1, min(batch, 5))
+            exhausted = (m_chk >= n) or (b[m_chk - 1] <= 1e-14 * max(1.0, np.abs(theta_all).max()))
+            done = bool(np.all(resid <= tol * np.maximum(np.abs(theta), 1e-3)) or exhausted)
+            if sharded:
+                # the ranks run identical kernels on identical data, so they agree; rank 0's word is taken anyway,
+                # because a disagreement would leave the all-gathers of the next batch unmatched
+                ctl = torch.tensor([int(done), step_batch], dtype=torch.int64, device=V.device)
+                _dist.broadcast_(ctl)
+                done, step_batch = bool(ctl[0].item()), int(ctl[1].item())
+            if done:
+                break
+        if done:
+            m = m_chk                                # steps run beyond the batch that was looked at are not used
         if done:
             info["converged"] = True
             break
