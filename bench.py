@@ -228,7 +228,7 @@ class ClockSampler:
         return out
 
 
-STAGES = ["knn_total", "knn_candidates", "knn_rerank", "kernel_build", "eigensolver", "lanczos_steps", "ritz_vectors",
+STAGES = ["knn_total", "knn_balance", "knn_candidates", "knn_rerank", "kernel_build", "eigensolver", "lanczos_steps", "ritz_vectors",
           "maxmin_sampling", "knn_direct", "graph_build", "sssp_partition", "sssp_tables", "sssp_overlay", "sssp",
           "sssp_expand", "refine", "markov_chain", "absorption_solve", "project"]
 SSSP_STAGES = ("sssp_partition", "sssp_tables", "sssp_overlay", "sssp", "sssp_expand")

@@ -421,6 +421,49 @@ def knn_direct(data: torch.Tensor, k: int, q0: int = 0, nq: Optional[int] = None
     return out_idx, out_dist
 
 
+KNN_BALANCE_MIN_ROWS = 262144
+
+
+def balanced_knn_bounds(prep: KnnPrep, k: int, slack: int = 12):
+    """Row boundaries (multiples of 256, in work order) that give every rank the same share of the candidate
+    kernel's work, or None (one rank, small input, SIMT engine).  The work of a 128-row query tile is the number of
+    reference tiles it visits -- 5 % to 25 % of them depending on where along the trajectory it lies -- so equal
+    row counts leave the slowest rank ~20 % behind the mean (measured: 85.7 ms against 70.5 at 2 GPUs, 26.2 against
+    17.6 at 8).  One wave of sampled query tiles (every ceil(T/148)-th) is run through the kernel itself
+    (pb200_knn_tc_visit_counts, ~3 ms), the visit counts are interpolated along the work order and the rows are cut at
+    equal cumulative counts.  Rank 0's cut is broadcast: the counts depend on the timing of the pruning bound."""
+    from . import _dist
+
+    rank, size = _dist.world()
+    n = prep.n
+    if size == 1 or prep.xtc is None or n < KNN_BALANCE_MIN_ROWS or k > KNN_MAX_KEEP:
+        return None
+    k_keep = min(KNN_MAX_KEEP, k + slack)
+    n_qt = (n + 127) // 128
+    stride = max(1, -(-n_qt // 148))
+    sample = torch.arange(stride // 2, n_qt, stride, dtype=I32, device=prep.yn.device)
+    ns = int(sample.numel())
+    counts = zeros((ns,), I32)
+    cand = empty((ns * 128, k_keep), I32)
+    score = empty((ns * 128, k_keep), F32)
+    thr = empty((ns * 128,), F32)
+    with stage("knn_balance"):
+        call("pb200_knn_tc_visit_counts", prep.xtc, prep.ld, prep.yn, prep.xcn, prep.box_lo, prep.box_hi, n, prep.d,
+             k_keep, sample, ns, cand, score, thr, counts)
+        work = np.interp(np.arange(n_qt), sample.cpu().numpy().astype(np.float64),
+                         np.maximum(counts.cpu().numpy().astype(np.float64), 1.0))
+    cum = np.concatenate([[0.0], np.cumsum(work)])
+    cuts = [0]
+    for r in range(1, size):
+        t = int(np.searchsorted(cum, cum[-1] * r / size))
+        t = max(cuts[-1] // 128, min(n_qt, (t + 1) // 2 * 2))          # whole pairs of query tiles (256 rows)
+        cuts.append(min(n, t * 128))
+    cuts.append(n)
+    b = torch.tensor(cuts, dtype=torch.int64, device=prep.yn.device)
+    _dist.broadcast_(b)
+    return [int(v) for v in b.tolist()]
+
+
 def knn_like_sklearn(x: torch.Tensor, n_neighbors: int, shard: bool = False):
     """Full self-including neighbour table, dispatching exactly as sklearn's algorithm='auto' would
     (see sklearn_uses_brute).  With shard=True the query rows are split across the ranks of the
@@ -431,9 +474,14 @@ def knn_like_sklearn(x: torch.Tensor, n_neighbors: int, shard: bool = False):
     q0, nq = _dist.row_shard(n, 256) if shard else (0, n)
     if sklearn_uses_brute(n, d, n_neighbors):
         prep = knn_prepare(x)
+        bounds = balanced_knn_bounds(prep, n_neighbors) if shard else None
+        if bounds is not None:
+            rank = _dist.world()[0]
+            q0, nq = bounds[rank], bounds[rank + 1] - bounds[rank]
         idx, dist, stats = knn_expanded(prep, n_neighbors, q0, nq)
         if shard:
-            idx, dist = _dist.allgather_rows(idx, dist, n, 256)
+            idx, dist = _dist.allgather_rows(idx, dist, n, 256, bounds)
+            stats["shard_rows"] = nq
         idx, dist = knn_unpermute(prep, idx, dist)
         stats["method"] = "expanded"
         if prep.perm is not None:

@@ -37,13 +37,14 @@ def row_shard(n: int, align: int = 1) -> Tuple[int, int]:
     return b[rank], b[rank + 1] - b[rank]
 
 
-def allgather_rows(idx: torch.Tensor, val: torch.Tensor, n: int, align: int = 1):
-    """Gather row shards (idx [nq,k], val [nq,k]) produced under ``row_shard(n, align)`` into
-    full [n,k] tables on every rank (uneven shards are padded to the largest one)."""
+def allgather_rows(idx: torch.Tensor, val: torch.Tensor, n: int, align: int = 1, bounds=None):
+    """Gather row shards (idx [nq,k], val [nq,k]) produced under ``row_shard(n, align)`` -- or under the explicit
+    ``bounds`` (size+1 row boundaries) -- into full [n,k] tables on every rank (uneven shards are padded to the
+    largest one)."""
     rank, size = world()
     if size == 1:
         return idx, val
-    b = shard_bounds(n, size, align)
+    b = list(bounds) if bounds is not None else shard_bounds(n, size, align)
     most = max(b[r + 1] - b[r] for r in range(size))
     outs = []
     for t in (idx, val):

@@ -71,6 +71,8 @@ struct TcParams {
   float* out_score;
   float* out_thr;
   unsigned long long* tiles_visited;
+  const int* qtile_list;  // optional: query tile (relative to q0) of every CTA of the launch
+  int* cta_visited;       // optional: reference tiles visited, per CTA
 };
 
 struct TcCtl {
@@ -303,17 +305,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
   const int CAP = p.cap, LSTRIDE = p.cap + 1, HIGH = p.cap - 32;
   TcCtl& ctl = *reinterpret_cast<TcCtl*>(lists + TC_BM * LSTRIDE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qbase = p.q0 + blockIdx.x * TC_BM;
-  const int row_local0 = blockIdx.x * TC_BM;
+  // query tile of this CTA: the blockIdx-th of the launch, or the one listed (sampled launches: pb200_knn_tc_visit_counts)
+  const int qrow0 = (p.qtile_list ? p.qtile_list[blockIdx.x] : (int)blockIdx.x) * TC_BM;   // first query row, relative to q0
+  const int qbase = p.q0 + qrow0;
+  const int row_local0 = blockIdx.x * TC_BM;       // first output row
   const int qtile = qbase / TC_BN;
   const int KCH = p.kch, NST = p.nst, T = p.n_tiles;
 
   for (int r = tid; r < TC_BM; r += TC_THREADS) {
     ctl.cnt[r] = 0;
     ctl.thr[r] = INFINITY;
-    ctl.xcn[r] = (row_local0 + r < p.nq) ? __double2float_ru(p.xcn[qbase + r]) : -INFINITY;
+    ctl.xcn[r] = (qrow0 + r < p.nq) ? __double2float_ru(p.xcn[qbase + r]) : -INFINITY;
   }
-  if (tid < 4) ctl.warp_bound[tid] = (row_local0 + tid * 32 < p.nq) ? INFINITY : -INFINITY;
+  if (tid < 4) ctl.warp_bound[tid] = (qrow0 + tid * 32 < p.nq) ? INFINITY : -INFINITY;
   if (tid == 0) {
     mbar_init(&ctl.a_full, 4);
     for (int s = 0; s < NST; ++s) { mbar_init(&ctl.b_full[s], 1); mbar_init(&ctl.b_empty[s], 1); }
@@ -429,6 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
       tslot = (tslot + 1) & 15;
     }
     if (lane == 0 && p.tiles_visited) atomicAdd(p.tiles_visited, visited);
+    if (lane == 0 && p.cta_visited) p.cta_visited[blockIdx.x] = (int)visited;
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (tc_elect_one()) {
@@ -632,7 +637,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
     for (int l = 0; l < 32; ++l) {
       const int r = quarter * 32 + l;
       const int grow = row_local0 + r;
-      if (grow >= p.nq) continue;
+      if (qrow0 + r >= p.nq) continue;
       tc_compact_row(&ctl, lists + r * LSTRIDE, r, p.k_keep, lane, CAP);   // leaves <= k_keep <= 48 entries
       int c = ctl.cnt[r];
       c = c < 64 ? c : 64;
@@ -789,10 +794,11 @@ int pb200_knn_tc_list_cap(void) { return 1; }   // candidate buffers live in sha
 
 // Tensor-core version of pb200_knn_candidates_f32 (same outputs; q0 % 128 == 0; lists:
 // ceil(nq/128)*128*pb200_knn_tc_list_cap() words).
-int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, const double* xcn,
-                            const double* box_lo, const double* box_hi, int q0, int nq, int d, int k_keep,
-                            unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
-                            unsigned long long* tiles_visited, void* stream) {
+static int launch_knn_tc(const float* xtc, long long n_pad, const float* yn, const double* xcn,
+                         const double* box_lo, const double* box_hi, int q0, int nq, int d, int k_keep,
+                         unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
+                         unsigned long long* tiles_visited, const int* qtile_list, int n_list, int* cta_visited,
+                         void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int d8 = (d + 7) / 8 * 8;
   if (d8 > 128 || k_keep < 1 || k_keep > TC_MAX_KEEP || q0 % TC_BM != 0 || n_pad % 256 != 0) {
@@ -807,6 +813,8 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   p.tail_steps = (d8 % 16 == 8) ? 1 : 2;
   p.k_keep = k_keep; p.lists = lists; p.out_idx = out_idx; p.out_score = out_score; p.out_thr = out_thr;
   p.tiles_visited = tiles_visited;
+  p.qtile_list = qtile_list;
+  p.cta_visited = cta_visited;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("PB200_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -830,9 +838,30 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
   const int smem = nst * TC_STAGE + TC_BM * (cap + 1) * 8 + (int)sizeof(TcCtl) + 64;
   if (smem > 227 * 1024) { set_error_msg("pb200_knn_candidates_tc: ring depth x candidate buffers exceed shared memory"); return -1; }
   PB_CHECK(cudaFuncSetAttribute(knn_candidates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  knn_candidates_tc_kernel<<<div_up(nq, TC_BM), TC_THREADS, smem, st>>>(p);
+  knn_candidates_tc_kernel<<<qtile_list ? n_list : div_up(nq, TC_BM), TC_THREADS, smem, st>>>(p);
   PB_CHECK_LAUNCH("knn_candidates_tc_kernel");
   return 0;
+}
+
+int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, const double* xcn,
+                            const double* box_lo, const double* box_hi, int q0, int nq, int d, int k_keep,
+                            unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
+                            unsigned long long* tiles_visited, void* stream) {
+  return launch_knn_tc(xtc, n_pad, yn, xcn, box_lo, box_hi, q0, nq, d, k_keep, lists, out_idx, out_score, out_thr,
+                       tiles_visited, nullptr, 0, nullptr, stream);
+}
+
+// The candidate kernel on a SAMPLE of query tiles (qtiles[n_list], each < ceil(n / 128)): counts[i] = reference tiles
+// the CTA of qtiles[i] visited.  The ranks of a sharded run cut the query rows where the cumulative counts are equal
+// (the work of a query tile is the tiles it visits: 5 % to 25 % of them along a trajectory).  Scratch outputs:
+// out_idx / out_score [n_list * 128 * k_keep], out_thr [n_list * 128].
+int pb200_knn_tc_visit_counts(const float* xtc, long long n_pad, const float* yn, const double* xcn,
+                              const double* box_lo, const double* box_hi, long long n, int d, int k_keep,
+                              const int* qtiles, int n_list, int* out_idx, float* out_score, float* out_thr,
+                              int* counts, void* stream) {
+  if (n_list <= 0) return 0;
+  return launch_knn_tc(xtc, n_pad, yn, xcn, box_lo, box_hi, 0, (int)n, d, k_keep, nullptr, out_idx, out_score, out_thr,
+                       nullptr, qtiles, n_list, counts, stream);
 }
 
 int pb200_tf32_peak_rot(int blocks, int iters, int rot, void* stream);
