@@ -12,7 +12,7 @@ from __future__ import annotations
 import math
 import os
 from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -429,6 +429,21 @@ def knn_direct(data: torch.Tensor, k: int, q0: int = 0, nq: Optional[int] = None
 KNN_BALANCE_MIN_ROWS = 262144
 
 
+def cuts_at_equal_work(work: np.ndarray, parts: int, n: int) -> List[int]:
+    """parts + 1 row boundaries over range(n) from the work of every 128-row tile: interior boundaries are whole pairs
+    of tiles (multiples of 256 rows, the alignment knn_expanded needs), monotone, and split the cumulative work into
+    equal shares as closely as that granularity allows."""
+    n_t = len(work)
+    cum = np.concatenate([[0.0], np.cumsum(np.asarray(work, dtype=np.float64))])
+    cuts = [0]
+    for r in range(1, parts):
+        t = int(np.searchsorted(cum, cum[-1] * r / parts))
+        t = max(cuts[-1] // 128, min(n_t, (t + 1) // 2 * 2))
+        cuts.append(min(n, t * 128))
+    cuts.append(n)
+    return cuts
+
+
 def balanced_knn_bounds(prep: KnnPrep, k: int, slack: int = 12):
     """Row boundaries (multiples of 256, in work order) that give every rank the same share of the candidate
     kernel's work, or None (one rank, small input, SIMT engine).  The work of a 128-row query tile is the number of
@@ -457,13 +472,7 @@ def balanced_knn_bounds(prep: KnnPrep, k: int, slack: int = 12):
              k_keep, sample, ns, cand, score, thr, counts)
         work = np.interp(np.arange(n_qt), sample.cpu().numpy().astype(np.float64),
                          np.maximum(counts.cpu().numpy().astype(np.float64), 1.0))
-    cum = np.concatenate([[0.0], np.cumsum(work)])
-    cuts = [0]
-    for r in range(1, size):
-        t = int(np.searchsorted(cum, cum[-1] * r / size))
-        t = max(cuts[-1] // 128, min(n_qt, (t + 1) // 2 * 2))          # whole pairs of query tiles (256 rows)
-        cuts.append(min(n, t * 128))
-    cuts.append(n)
+    cuts = cuts_at_equal_work(work, size, n)
     b = torch.tensor(cuts, dtype=torch.int64, device=prep.yn.device)
     _dist.broadcast_(b)
     return [int(v) for v in b.tolist()]

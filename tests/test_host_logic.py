@@ -417,3 +417,29 @@ def test_install_patches_an_installed_reference(monkeypatch):
     assert ref.core.run_palantir is palantir_b200.core.run_palantir and ref.run_palantir is palantir_b200.core.run_palantir
     assert ref.utils.run_density is sentinel and ref.plot.plot_palantir_results is sentinel      # off the path: untouched
     assert ref.presults.PResults is palantir_b200.PResults
+
+
+def test_knn_shard_cuts_at_equal_work():
+    """Row boundaries of the sharded kNN from per-tile work: aligned, monotone, complete, balanced."""
+    from palantir_b200._device import cuts_at_equal_work
+
+    rng = np.random.default_rng(0)
+    n = 1_000_000
+    n_t = (n + 127) // 128
+    # work density as along a branching trajectory: between 5 % and 25 % of the tiles visited
+    work = 400 + 1500 * (0.5 + 0.5 * np.sin(np.linspace(0, 7, n_t))) + rng.integers(0, 50, n_t)
+    for parts in (2, 3, 4, 8):
+        cuts = cuts_at_equal_work(work, parts, n)
+        assert len(cuts) == parts + 1 and cuts[0] == 0 and cuts[-1] == n
+        assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+        assert all(c % 256 == 0 for c in cuts[1:-1])
+        share = [work[a // 128:(b + 127) // 128].sum() for a, b in zip(cuts, cuts[1:])]
+        assert max(share) / (work.sum() / parts) < 1.01
+        even = [work[a // 128:(b + 127) // 128].sum() for a, b in zip(range(0, n, n // parts), range(n // parts, n + 1, n // parts))]
+        assert max(even) / (work.sum() / parts) > 1.05          # what equal row counts would have given
+    # degenerate inputs: all the work in one tile, fewer tile pairs than parts
+    w = np.zeros(100); w[7] = 1.0
+    cuts = cuts_at_equal_work(w, 4, 100 * 128 - 5)
+    assert cuts[0] == 0 and cuts[-1] == 100 * 128 - 5 and all(a <= b for a, b in zip(cuts, cuts[1:]))
+    cuts = cuts_at_equal_work(np.ones(3), 8, 300)
+    assert cuts[0] == 0 and cuts[-1] == 300 and all(a <= b for a, b in zip(cuts, cuts[1:])) and max(cuts) == 300
