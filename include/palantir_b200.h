@@ -91,12 +91,14 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
                             unsigned long long* tiles_visited, void* stream);
 
 /* the same kernel on a sample of query tiles (qtiles[n_list], each < ceil(n / 128)): counts[i] = reference tiles the
- * CTA of qtiles[i] visited -- the ranks of a sharded run cut the query rows where the cumulative counts are equal.
+ * CTA of qtiles[i] visited (visit_limit = 0), or the tiles visited up to visit_limit plus those that still pass the
+ * box test against the bound reached by then (an estimate at visit_limit tiles per CTA) -- the ranks of a sharded
+ * run cut the query rows where the cumulative counts are equal.
  * Scratch outputs: out_idx / out_score [n_list * 128 * k_keep], out_thr [n_list * 128] */
 int pb200_knn_tc_visit_counts(const float* xtc, long long n_pad, const float* yn, const double* xcn,
                               const double* box_lo, const double* box_hi, long long n, int d, int k_keep,
-                              const int* qtiles, int n_list, int* out_idx, float* out_score, float* out_thr,
-                              int* counts, void* stream);
+                              const int* qtiles, int n_list, int visit_limit, int* out_idx, float* out_score,
+                              float* out_thr, int* counts, void* stream);
 
 /* rows_out[0..counter) = indices (relative to q0) of flagged rows. */
 /* TF32 tensor peak probe: blocks CTAs x iters bare tcgen05.mma.kind::tf32 128x128x8 instructions (262144 FLOP each);

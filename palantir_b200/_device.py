@@ -427,6 +427,9 @@ def knn_direct(data: torch.Tensor, k: int, q0: int = 0, nq: Optional[int] = None
 
 
 KNN_BALANCE_MIN_ROWS = 262144
+# sampled query tiles fetch this many reference tiles, then only count the tiles their pruning bound still admits
+# (0: they run to the end -- one CTA lifetime, ~2.7 ms at 1 M cells, against ~0.1 ms)
+KNN_BALANCE_VISIT_LIMIT = int(os.environ.get("PB200_KNN_BALANCE_LIMIT", "24"))
 
 
 def cuts_at_equal_work(work: np.ndarray, parts: int, n: int) -> List[int]:
@@ -450,8 +453,8 @@ def balanced_knn_bounds(prep: KnnPrep, k: int, slack: int = 12):
     reference tiles it visits -- 5 % to 25 % of them depending on where along the trajectory it lies -- so equal
     row counts leave the slowest rank ~20 % behind the mean (measured: 85.7 ms against 70.5 at 2 GPUs, 26.2 against
     17.6 at 8).  One wave of sampled query tiles (every ceil(T/148)-th) is run through the kernel itself
-    (pb200_knn_tc_visit_counts, ~3 ms), the visit counts are interpolated along the work order and the rows are cut at
-    equal cumulative counts.  Rank 0's cut is broadcast: the counts depend on the timing of the pruning bound."""
+    (pb200_knn_tc_visit_counts) for KNN_BALANCE_VISIT_LIMIT tiles each and then counts the tiles its pruning bound
+    still admits; the counts are interpolated along the work order and the rows are cut at equal cumulative counts.  Rank 0's cut is broadcast: the counts depend on the timing of the pruning bound."""
     from . import _dist
 
     rank, size = _dist.world()
@@ -469,7 +472,7 @@ def balanced_knn_bounds(prep: KnnPrep, k: int, slack: int = 12):
     thr = empty((ns * 128,), F32)
     with stage("knn_balance"):
         call("pb200_knn_tc_visit_counts", prep.xtc, prep.ld, prep.yn, prep.xcn, prep.box_lo, prep.box_hi, n, prep.d,
-             k_keep, sample, ns, cand, score, thr, counts)
+             k_keep, sample, ns, KNN_BALANCE_VISIT_LIMIT, cand, score, thr, counts)
         work = np.interp(np.arange(n_qt), sample.cpu().numpy().astype(np.float64),
                          np.maximum(counts.cpu().numpy().astype(np.float64), 1.0))
     cuts = cuts_at_equal_work(work, size, n)

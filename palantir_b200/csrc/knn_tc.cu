@@ -73,6 +73,8 @@ struct TcParams {
   unsigned long long* tiles_visited;
   const int* qtile_list;  // optional: query tile (relative to q0) of every CTA of the launch
   int* cta_visited;       // optional: reference tiles visited, per CTA
+  int visit_limit;        // > 0 (sampled launches): after this many tiles the producer only COUNTS the tiles that pass
+                          // the box test against the bound reached so far, without fetching them
 };
 
 struct TcCtl {
@@ -408,6 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_candidates_tc_kernel(const 
         break;
       }
       ++visited;
+      if (p.visit_limit > 0 && visited > (unsigned long long)p.visit_limit) continue;   // counted, not fetched
       if (issuer) {
         ctl.tile_ring[tslot] = chosen;           // published by the release of the first stage's arrive
         const float* src = p.xtc + (long long)chosen * KCH * (TC_STAGE / 4);
@@ -798,7 +801,7 @@ static int launch_knn_tc(const float* xtc, long long n_pad, const float* yn, con
                          const double* box_lo, const double* box_hi, int q0, int nq, int d, int k_keep,
                          unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
                          unsigned long long* tiles_visited, const int* qtile_list, int n_list, int* cta_visited,
-                         void* stream) {
+                         int visit_limit, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int d8 = (d + 7) / 8 * 8;
   if (d8 > 128 || k_keep < 1 || k_keep > TC_MAX_KEEP || q0 % TC_BM != 0 || n_pad % 256 != 0) {
@@ -815,6 +818,7 @@ static int launch_knn_tc(const float* xtc, long long n_pad, const float* yn, con
   p.tiles_visited = tiles_visited;
   p.qtile_list = qtile_list;
   p.cta_visited = cta_visited;
+  p.visit_limit = visit_limit;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("PB200_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -848,20 +852,22 @@ int pb200_knn_candidates_tc(const float* xtc, long long n_pad, const float* yn, 
                             unsigned long long* lists, int* out_idx, float* out_score, float* out_thr,
                             unsigned long long* tiles_visited, void* stream) {
   return launch_knn_tc(xtc, n_pad, yn, xcn, box_lo, box_hi, q0, nq, d, k_keep, lists, out_idx, out_score, out_thr,
-                       tiles_visited, nullptr, 0, nullptr, stream);
+                       tiles_visited, nullptr, 0, nullptr, 0, stream);
 }
 
 // The candidate kernel on a SAMPLE of query tiles (qtiles[n_list], each < ceil(n / 128)): counts[i] = reference tiles
-// the CTA of qtiles[i] visited.  The ranks of a sharded run cut the query rows where the cumulative counts are equal
+// the CTA of qtiles[i] visited -- or, with visit_limit > 0, the tiles it visited up to that limit plus the tiles that
+// still pass the box test against the pruning bound reached by then (an estimate that costs visit_limit tiles per CTA
+// instead of ~1000; the bound after a dozen tiles is looser than the final one, alike for every query tile).  The ranks of a sharded run cut the query rows where the cumulative counts are equal
 // (the work of a query tile is the tiles it visits: 5 % to 25 % of them along a trajectory).  Scratch outputs:
 // out_idx / out_score [n_list * 128 * k_keep], out_thr [n_list * 128].
 int pb200_knn_tc_visit_counts(const float* xtc, long long n_pad, const float* yn, const double* xcn,
                               const double* box_lo, const double* box_hi, long long n, int d, int k_keep,
-                              const int* qtiles, int n_list, int* out_idx, float* out_score, float* out_thr,
-                              int* counts, void* stream) {
+                              const int* qtiles, int n_list, int visit_limit, int* out_idx, float* out_score,
+                              float* out_thr, int* counts, void* stream) {
   if (n_list <= 0) return 0;
   return launch_knn_tc(xtc, n_pad, yn, xcn, box_lo, box_hi, 0, (int)n, d, k_keep, nullptr, out_idx, out_score, out_thr,
-                       nullptr, qtiles, n_list, counts, stream);
+                       nullptr, qtiles, n_list, counts, visit_limit, stream);
 }
 
 int pb200_tf32_peak_rot(int blocks, int iters, int rot, void* stream);
