@@ -238,6 +238,7 @@ SSSP_STAGES = ("sssp_partition", "sssp_tables", "sssp_overlay", "sssp", "sssp_ex
 NCU_TRAFFIC_C3 = {
     "knn_candidates_tc_kernel": (1.706e11, "profiles/r2_knn_tc_ncu.md"),
     "csr_spmv_stream_kernel": (6.617e8, "profiles/r2_spmv_ncu.md"),
+    "sssp_cells_stage": (1.931e10, "profiles/r2_sssp_cells_ncu.md"),     # grow + local + overlay search + expansion
 }
 
 
@@ -492,7 +493,11 @@ def run_gpu_arm(args):
                      "arcs_per_s": n_src * n_arcs / (sssp_ms / 1e3), "ms": sssp_ms, "share_of_step": sssp_ms / ms_step,
                      "parts_ms": {k: prof.get(k) for k in SSSP_STAGES if k in prof},
                      "overlay_rounds_mean": sssp_info.get("rounds_mean"), "sources": n_src, "arcs": n_arcs,
-                     "cells": sssp_info.get("cells"), "traffic": None}
+                     "cells": sssp_info.get("cells"),
+                     "traffic": (NCU_TRAFFIC_C3["sssp_cells_stage"][0]
+                                 if (sssp_info.get("cells") and n == 1_000_000 and d == 100 and world == 1) else None),
+                     "traffic_source": (NCU_TRAFFIC_C3["sssp_cells_stage"][1]
+                                        if (sssp_info.get("cells") and n == 1_000_000 and d == 100 and world == 1) else None)}
 
     # the kernel with the largest share of the step is the line's `roofline`
     shares = {"knn": knn_ms if knn_ms == knn_ms else 0.0, "sssp": sssp_ms,
