@@ -169,6 +169,20 @@ assert torch.all(b == 0.0)
 # waypoint (source) shards cover all rows exactly once
 bounds = _dist.shard_bounds(1185, 2)
 assert bounds == [0, 592, 1185]
+# row shards cut at equal work (uneven, explicit boundaries), one of them empty on the way
+from palantir_b200._device import cuts_at_equal_work
+import numpy as np
+for cuts in (cuts_at_equal_work(np.r_[np.full(4, 10.0), np.full(4, 1.0)], 2, n), [0, 0, n], [0, 768, n]):
+    r = dist.get_rank()
+    a, b_ = cuts[r], cuts[r + 1]
+    gi, gd = _dist.allgather_rows(full_i[a:b_].clone(), full_d[a:b_].clone(), n, 256, cuts)
+    assert torch.equal(gi, full_i) and torch.equal(gd, full_d), ("allgather with explicit bounds", cuts)
+# the row-sharded eigensolver's exchange: every rank fills its slice of w, one in-place all-gather completes it
+chunk = 512
+w = torch.full((2 * chunk,), -1.0, dtype=torch.float64)
+w[dist.get_rank() * chunk:(dist.get_rank() + 1) * chunk] = torch.arange(chunk, dtype=torch.float64) + 1000.0 * dist.get_rank()
+dist.all_gather_into_tensor(w, w[dist.get_rank() * chunk:(dist.get_rank() + 1) * chunk])
+assert torch.equal(w, torch.cat([torch.arange(chunk, dtype=torch.float64), torch.arange(chunk, dtype=torch.float64) + 1000.0]))
 dist.destroy_process_group()
 print("ok", dist.get_rank() if False else sys.argv[3])
 '''
