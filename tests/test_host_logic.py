@@ -457,3 +457,17 @@ def test_knn_shard_cuts_at_equal_work():
     assert cuts[0] == 0 and cuts[-1] == 100 * 128 - 5 and all(a <= b for a, b in zip(cuts, cuts[1:]))
     cuts = cuts_at_equal_work(np.ones(3), 8, 300)
     assert cuts[0] == 0 and cuts[-1] == 300 and all(a <= b for a, b in zip(cuts, cuts[1:])) and max(cuts) == 300
+
+
+def test_bench_traffic_figures_point_at_committed_profiles():
+    """Every DRAM-traffic figure bench.py reports names the ncu summary it was read from; the file must be in the tree."""
+    import ast
+
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    table = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Assign) and any(getattr(t, "id", None) == "NCU_TRAFFIC_C3" for t in node.targets):
+            table = ast.literal_eval(node.value)
+    assert table and {"knn_candidates_tc_kernel", "csr_spmv_stream_kernel", "sssp_cells_stage"} <= set(table)
+    for kernel, (nbytes, source) in table.items():
+        assert nbytes > 0 and os.path.exists(os.path.join(ROOT, source)), (kernel, source)
