@@ -188,13 +188,20 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+# PB200_NVTX=1: every stage is also an NVTX range (names as in bench.py's stages_ms), so that `ncu --nvtx --nvtx-include
+# "knn_candidates/"` or an nsys timeline can address a stage by name
+NVTX_RANGES = os.environ.get("PB200_NVTX", "0") == "1"
+
+
 class _Timer:
-    """CUDA-event stage timer (only active when PROFILE is a dict)."""
+    """CUDA-event stage timer (only active when PROFILE is a dict) and, with PB200_NVTX=1, an NVTX range."""
 
     def __init__(self, name):
         self.name = name
 
     def __enter__(self):
+        if NVTX_RANGES:
+            torch.cuda.nvtx.range_push(self.name)
         if PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
@@ -205,6 +212,8 @@ class _Timer:
         if PROFILE is not None:
             self.e1.record()
             PROFILE.setdefault("_events", []).append((self.name, self.e0, self.e1))
+        if NVTX_RANGES:
+            torch.cuda.nvtx.range_pop()
         return False
 
 

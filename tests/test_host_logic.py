@@ -471,3 +471,23 @@ def test_bench_traffic_figures_point_at_committed_profiles():
     assert table and {"knn_candidates_tc_kernel", "csr_spmv_stream_kernel", "sssp_cells_stage"} <= set(table)
     for kernel, (nbytes, source) in table.items():
         assert nbytes > 0 and os.path.exists(os.path.join(ROOT, source)), (kernel, source)
+
+
+def test_stage_ranges_are_inert_by_default_and_nest_with_nvtx(monkeypatch):
+    """dv.stage(): no events and no NVTX calls unless asked for; with PB200_NVTX ranges are pushed and popped in pairs."""
+    import torch
+    from palantir_b200 import _device as dv
+
+    calls = []
+    monkeypatch.setattr(torch.cuda.nvtx, "range_push", lambda name: calls.append(("push", name)))
+    monkeypatch.setattr(torch.cuda.nvtx, "range_pop", lambda: calls.append(("pop",)))
+    monkeypatch.setattr(dv, "PROFILE", None)
+    monkeypatch.setattr(dv, "NVTX_RANGES", False)
+    with dv.stage("outer"):
+        pass
+    assert calls == []
+    monkeypatch.setattr(dv, "NVTX_RANGES", True)
+    with dv.stage("outer"):
+        with dv.stage("inner"):
+            pass
+    assert calls == [("push", "outer"), ("push", "inner"), ("pop",), ("pop",)]
