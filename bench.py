@@ -22,9 +22,10 @@ config 5 (run_magic_imputation, t = 3, 1 M cells x 2000 genes).
             same --steps / --warmup, so that the two lines can be compared like for like.
 `--impl reference`: times that CPU path alone and prints its own line.
 
-With N > 1 (torchrun, one process per GPU, NCCL) the job is split: kNN query rows and shortest-path sources
-are sharded, neighbour lists are all-gathered and the per-cell refinement sums all-reduced ("scaling":
-"strong" -- the job size is fixed).
+With N > 1 (torchrun, one process per GPU, NCCL) the job is split: kNN query rows (cut at equal work) and
+shortest-path sources are sharded, neighbour lists are all-gathered, the eigensolver's product is sharded by rows
+(one all-gather of an N-vector per step) and the per-cell refinement sums all-reduced ("scaling": "strong" -- the
+job size is fixed).  `traffic` figures are per-launch DRAM bytes read from the committed ncu summaries (NCU_TRAFFIC_C3).
 """
 from __future__ import annotations
 
